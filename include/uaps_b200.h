@@ -1,0 +1,155 @@
+/*
+ * uaps_b200.h -- C ABI of libuaps_b200.so: the UAPS unlabeled-batch hot path on B200 (sm_100a).
+ *
+ * The reference (djene-mengistu/UAPS) has no FFI: its hot path is Python over torch.nn.  This
+ * header is the boundary a maintainer binds *underneath* that Python surface (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference expression it replaces, with
+ * file:line relative to the reference checkout.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes; every buffer is allocated and owned by the CALLER; the library
+ *     never allocates device memory, never retains a pointer past the call, never synchronises
+ *     the host, and launches only on the stream it is given (re-entrant per device/stream);
+ *   - tensors are contiguous NCHW fp32 unless stated otherwise, exactly as the reference's
+ *     model emits them (utilities/UAPS_unet.py:224-233);
+ *   - return value: 0 = ok, negative = UAPS_E* (invalid argument), positive = cudaError_t of
+ *     the failed launch.  Nothing throws across the ABI.
+ */
+#ifndef UAPS_B200_H
+#define UAPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define UAPS_ABI_VERSION 1
+#define UAPS_KMAX 6              /* decoders: reference uses 4 (UAPS_unet.py:219-222); ablation up to 5 */
+#define UAPS_CMAX 8              /* classes: 4 NEU, 2 KoSDD2, 7 DAGM (DAGM-Dataset-codes/UAPS_model.py:11) */
+
+enum {
+    UAPS_OK = 0,
+    UAPS_EINVAL = -1,            /* null pointer, non-positive size */
+    UAPS_ERANGE = -2,            /* K, C or pixel count outside the supported range */
+    UAPS_EALIGN = -3,            /* pointer not aligned to its element type */
+    UAPS_ENODEV = -4             /* not running on an sm_100 device */
+};
+
+int         uaps_abi_version(void);
+const char* uaps_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused pseudo-label + KL-uncertainty + uncertainty-weighted CE/Dice loss
+ * replaces UAPS_train.py:186-189 (K softmaxes), :223 (mean prediction), :226-236 (KL maps and
+ * exp(-KL)), :241-243 (uncertainty loss), :251-255 (Dirichlet mix + argmax), :259-262 with
+ * utilities/pytorch_losses.py:54-89 (CE + Dice per decoder), :265-277 (uncertainty weighting),
+ * :282 (unlabeled part of the total) and their autograd backward (:287).
+ *
+ * Two passes are forced by the math: every per-pixel gradient needs batch-global scalars.
+ *   pass1    : read K logits tensors once, per-pixel softmax/KL/argmax in registers, warp-shuffle
+ *              + block partial sums, last block folds them to `sums` in fp64 (deterministic).
+ *   (N>1 GPUs: the caller all-reduces `sums` here -- the path's one data exchange.)
+ *   finalize : sums -> loss scalars.
+ *   pass2    : re-read logits, recompute per-pixel terms, write d(loss)/d(logits).
+ * Algorithmic HBM bytes per unlabeled pixel: pass1 4KC, pass2 8KC (read 4KC + write 4KC).
+ * ------------------------------------------------------------------------------------------- */
+
+/* number of doubles in `sums`: [K] sum(-logp[y]) | [K] sum(E_k) | [K] sum(V_k) | [K*C] I_kc |
+ * [K*C] sum(p_kc) | [C] T_c = count(y == c). */
+int    uaps_loss_sums_count(int K, int C);
+/* number of floats in `scalars` (layout: UAPS_SC_* below). */
+int    uaps_loss_scalars_count(int K, int C);
+/* bytes of scratch `workspace` pass1 needs.  Must be zero-filled ONCE by the caller before its
+ * first use; every call leaves it ready for the next one. */
+size_t uaps_loss_workspace_bytes(int K, int C);
+
+/* scalars[] layout */
+#define UAPS_SC_LOSS_U   0       /* cw1 * ps_loss + cw2 * l_uncert      (UAPS_train.py:282)      */
+#define UAPS_SC_PS_LOSS  1       /* (1/K) sum_k ps_k * mean(E_k)        (:265-277)               */
+#define UAPS_SC_L_UNCERT 2       /* mean((1/K) sum_k V_k)               (:241-243)               */
+#define UAPS_SC_CW1      3
+#define UAPS_SC_CW2      4
+#define UAPS_SC_INV_N    5       /* 1 / N_global                                                   */
+#define UAPS_SC_MEAN_CE  6       /* mean_k CE_k    (total_loss_ce,   UAPS_train.py:216)            */
+#define UAPS_SC_MEAN_DICE 7      /* mean_k Dice_k  (total_loss_dice, UAPS_train.py:217)            */
+#define UAPS_SC_BASE     8       /* then ps_k[K], Ebar_k[K], CE_k[K], Dice_k[K], I_kc[K*C], Card_kc[K*C] */
+
+/* flags for pass1 / pass2 (must be the same in both).
+ * default (0): MUFU-based exp2/log2/rcp arithmetic, values within ~1e-6 relative of the fp32
+ *   reference; the pseudo-label is STILL bit-exact with torch.argmax: pixels whose top-two mixed
+ *   probabilities are closer than 2e-5 are re-decided with the exact torch-order chain.
+ * UAPS_LOSS_EXACT: every softmax uses torch's op order and IEEE expf/div/logf (validation mode,
+ *   about half the speed). */
+#define UAPS_LOSS_EXACT 1
+
+/* z: host array of K device pointers, each [B,C,HW] fp32.  mix_w: host array of K floats (the
+ * Dirichlet draw of :251, already rounded to fp32 as torch rounds a python scalar).
+ * labels: NULL for the unlabeled path (pseudo-label = argmax of the mix); else device int64
+ * [B,HW] ground truth -> supervised mode (UAPS_train.py:194-218: no KL terms, E_k = 1).
+ * pseudo_out: nullable device int64 [B,HW] (torch.argmax result, lowest index on ties).
+ * exp_var_out: nullable host array of K device pointers [B,HW] fp32 receiving exp(-V_k). */
+int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t HW,
+                    const float* mix_w, const int64_t* labels,
+                    void* workspace, double* sums,
+                    int64_t* pseudo_out, float* const* exp_var_out, int flags, cudaStream_t stream);
+
+/* sums_global: device, uaps_loss_sums_count doubles (all-reduced over ranks by the caller when
+ * the batch is sharded); N_global = total pixels behind those sums.  supervised != 0 selects
+ * the labeled-batch formula (scalars[LOSS_U] = mean_k 0.5(CE_k + Dice_k), cw ignored). */
+int uaps_loss_finalize(const double* sums_global, int K, int C, int64_t N_global,
+                       float cw1, float cw2, int supervised, float* scalars, cudaStream_t stream);
+
+/* grad_out: device, laid out like scalars[]: the upstream gradients of the five differentiable
+ * slots LOSS_U, PS_LOSS, L_UNCERT, MEAN_CE, MEAN_DICE are read, the rest ignored (so the autograd
+ * gradient of the scalars vector can be passed as is).
+ * dz: host array of K device pointers [B,C,HW] fp32, overwritten. */
+int uaps_loss_pass2(const float* const* z, int K, int B, int C, int64_t HW,
+                    const float* mix_w, const int64_t* labels,
+                    const float* scalars, const float* grad_out,
+                    float* const* dz, int flags, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Encoder-feature perturbations (utilities/UAPS_unet.py:156-185, applied at :227-231).
+ * x, y: [B, C, HW] fp32 (C*HW = `chw` elements per sample where only that matters).
+ * Randomness is either INJECTED (a caller-provided tensor, used for parity with the reference's
+ * draws) or generated in-kernel from a Philox4x32-10 counter keyed by (seed, element index), so
+ * forward and backward regenerate the same draw and no mask is ever stored.
+ * ------------------------------------------------------------------------------------------- */
+
+/* FeatureNoise :172-185: y = x * n + x, n ~ U(-range, range) of shape [C,HW], shared by the batch.
+ * noise == NULL -> Philox(seed).  The same entry point is its backward (dx = g * n + g). */
+int uaps_feature_noise(const float* x, const float* noise, uint64_t seed, float range,
+                       float* y, int B, int64_t chw, cudaStream_t stream);
+
+/* F.dropout(x, p) with training=True (:156-158) and nn.Dropout(p) of the encoder blocks (:40):
+ * y = x * keep / (1 - p).  keep (uint8 [B*chw]) == NULL -> Philox(seed).  Also its own backward. */
+int uaps_dropout(const float* x, const uint8_t* keep, uint64_t seed, double p,
+                 float* y, int64_t n, cudaStream_t stream);
+
+/* FeatureDropout :161-169, phase 1: attention[b,hw] = mean_c x[b,c,hw]; smax[b] = max_hw attention.
+ * smax_enc (B uint32, order-preserving encoding of the float max) must be zeroed by the caller. */
+int uaps_fdrop_stats(const float* x, int B, int C, int64_t HW,
+                     float* attention, uint32_t* smax_enc, cudaStream_t stream);
+/* phase 2: y = x * (attention < smax * u), u = the single U(0.7,0.9) draw of :165 (host float).
+ * With x := upstream gradient it is the backward (the comparison carries no gradient). */
+int uaps_fdrop_apply(const float* x, const float* attention, const uint32_t* smax_enc, float u,
+                     float* y, int B, int C, int64_t HW, cudaStream_t stream);
+
+/* All three at once for one feature level: x is read once, three perturbed copies are written
+ * (16 B/element instead of 24).  Any of y_noise / y_drop / y_fdrop may be NULL. */
+int uaps_perturb3(const float* x, const float* noise, const uint8_t* keep, uint64_t seed,
+                  float noise_range, double p_drop, const float* attention,
+                  const uint32_t* smax_enc, float u,
+                  float* y_noise, float* y_drop, float* y_fdrop,
+                  int B, int C, int64_t HW, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAPS_B200_H */

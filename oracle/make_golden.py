@@ -277,7 +277,7 @@ def golden_unet(ref_unet):
         assert torch.allclose(g_ref, g_mine, rtol=2e-3, atol=2e-4 * g_ref.abs().max().item() + 1e-7), n
         gsum.append(g_ref.sum().item())
         gnorm.append(g_ref.norm().item())
-    keep_full = ["encoder.in_conv.conv_conv.0.weight", "encoder.down4.maxpool_conv.1.conv_conv.4.weight",
+    keep_full = ["encoder.in_conv.conv_conv.0.weight", "encoder.down2.maxpool_conv.1.conv_conv.4.weight",
                  "main_decoder.out_conv.weight", "aux_decoder1.up1.conv1x1.weight",
                  "aux_decoder3.up4.conv.conv_conv.1.weight", "aux_decoder2.up2.conv.conv_conv.5.bias"]
     pg = dict(model.named_parameters())

@@ -1,0 +1,222 @@
+"""GPU parity: the fused loss kernels, called through the C ABI, against the oracle.
+
+Three layers of evidence:
+  1. committed golden vectors (generated from the reference's own executed lines);
+  2. the oracle run on the same device (torch CUDA eager) on seeded inputs -- this is the bit-exact
+     comparator for the pseudo-label, since torch's CPU (Sleef) and CUDA expf differ in the last ulp;
+  3. size-independent properties at BASELINE.json's full sizes (sharding invariance, label
+     consistency between the two passes, gradient sum identities).
+Tolerances: pseudo-label exact; scalars 1e-5 relative; maps and gradients 1e-5 of the tensor's scale.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.uaps_loss_ref import (dice_loss_ref, supervised_loss_ref, unlabeled_loss_fp64_closed_form,
+                                  unlabeled_loss_ref)
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _assert_close(a, b, what, rel=REL):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    scale = b.abs().max().item() + 1e-30
+    err = (a - b).abs().max().item()
+    assert err <= rel * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def _ours(z, mix_w, cw1, cw2, exact, **kw):
+    from uaps_b200.losses import uaps_unlabeled_loss
+    zs = [t.detach().clone().requires_grad_(True) for t in z]
+    loss, ps, unc, pseudo, ev = uaps_unlabeled_loss(zs, mix_w, cw1, cw2, return_pseudo=True, return_exp_var=True,
+                                                    exact_math=exact, **kw)
+    loss.backward()
+    return dict(loss_u=loss, ps_loss=ps, l_uncert=unc, pseudo=pseudo, exp_var=ev, grads=[t.grad for t in zs])
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_golden_cases(loss_cases, exact):
+    dev = _dev()
+    for name, c in loss_cases.items():
+        if name.startswith("sup"):
+            continue
+        z = [torch.from_numpy(a).to(dev) for a in c["logits"]]
+        o = _ours(z, c["mix_w"], float(c["cw"][0]), float(c["cw"][1]), exact)
+        # golden labels come from CPU torch; the synthetic cases have no 1-ulp near-ties, exact ties are covered
+        assert np.array_equal(o["pseudo"].cpu().numpy(), c["pseudo"]), name
+        for key in ("loss_u", "ps_loss", "l_uncert"):
+            assert o[key].item() == pytest.approx(float(c[key]), rel=REL), (name, key, exact)
+        _assert_close(torch.stack(o["exp_var"]), torch.from_numpy(c["exp_var"]), f"{name} exp_var")
+        _assert_close(torch.stack(o["grads"]), torch.from_numpy(c["grads"]), f"{name} grads")
+
+
+@pytest.mark.parametrize("K,C,B,H,W,scale", [
+    (4, 4, 8, 200, 200, 2.0),        # NEU-Seg raw shape of BASELINE configs[1]
+    (4, 4, 4, 256, 256, 2.0),
+    (4, 2, 2, 232, 640, 2.0),        # KolektorSDD2 raw shape
+    (5, 2, 2, 256, 512, 2.0),
+    (2, 3, 3, 64, 64, 2.0),
+    (3, 4, 2, 33, 35, 2.0),          # odd HW -> scalar path
+    (6, 4, 2, 128, 128, 8.0),        # peaked
+    (4, 4, 4, 256, 256, 0.05),       # nearly uniform softmaxes: many near-ties -> exact-argmax fallback
+    (4, 7, 2, 64, 64, 2.0),          # DAGM class count in the reference (DAGM-Dataset-codes/UAPS_model.py:11)
+])
+@pytest.mark.parametrize("exact", [False, True])
+def test_against_oracle_on_device(K, C, B, H, W, scale, exact):
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(1337 + K * 10 + C)
+    z = [(torch.randn(B, C, H, W, generator=g) * scale).to(dev) for _ in range(K)]
+    mix_w = np.random.default_rng(1337).dirichlet(np.ones(K))
+    cw1, cw2 = 0.1, 0.1
+    zr = [t.clone().requires_grad_(True) for t in z]
+    ref = unlabeled_loss_ref(zr, mix_w, cw1, cw2)           # torch CUDA eager = the reference's GPU arithmetic
+    ref["loss_u"].backward()
+    o = _ours(z, mix_w, cw1, cw2, exact)
+    assert torch.equal(o["pseudo"], ref["pseudo"]), \
+        f"pseudo-label mismatches: {(o['pseudo'] != ref['pseudo']).sum().item()} of {ref['pseudo'].numel()}"
+    for key in ("loss_u", "ps_loss", "l_uncert"):
+        assert o[key].item() == pytest.approx(ref[key].item(), rel=REL), key
+    _assert_close(torch.stack(o["exp_var"]), torch.stack(ref["exp_var"]), "exp_var")
+    _assert_close(torch.stack(o["grads"]), torch.stack([t.grad for t in zr]), "grads")
+    # and the fp64 closed form, independent of autograd
+    cf = unlabeled_loss_fp64_closed_form(z, mix_w, cw1, cw2, ref["pseudo"])
+    _assert_close(torch.stack(o["grads"]), torch.stack(cf["dz"]), "grads vs fp64 closed form", rel=2e-5)
+
+
+def test_exact_ties_resolve_to_lowest_index():
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    z = []
+    for _ in range(4):
+        t = torch.randn(2, 4, 64, 64, generator=g)
+        t[:, 1] = t[:, 0]
+        t[:, 3] = t[:, 2]
+        z.append(t.to(dev))
+    mix_w = [0.1, 0.2, 0.3, 0.4]
+    ref = unlabeled_loss_ref(z, mix_w, 0.1, 0.1)
+    for exact in (False, True):
+        o = _ours(z, mix_w, 0.1, 0.1, exact)
+        assert torch.equal(o["pseudo"], ref["pseudo"])
+        assert set(o["pseudo"].unique().tolist()) <= {0, 2}
+
+
+def test_separate_upstream_gradients():
+    """ps_loss and l_uncert are differentiable on their own (the loop logs them, :298-299)."""
+    from uaps_b200.losses import uaps_unlabeled_loss
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    z = [(torch.randn(2, 4, 32, 32, generator=g) * 2).to(dev) for _ in range(4)]
+    mix_w = [0.4, 0.3, 0.2, 0.1]
+    for pick in ("ps_loss", "l_uncert"):
+        zr = [t.clone().requires_grad_(True) for t in z]
+        ref = unlabeled_loss_ref(zr, mix_w, 0.3, 0.2)
+        (2.5 * ref[pick]).backward()
+        zs = [t.clone().requires_grad_(True) for t in z]
+        _, ps, unc, _, _ = uaps_unlabeled_loss(zs, mix_w, 0.3, 0.2)
+        (2.5 * (ps if pick == "ps_loss" else unc)).backward()
+        _assert_close(torch.stack([t.grad for t in zs]), torch.stack([t.grad for t in zr]), pick)
+
+
+def test_supervised_golden_and_dropins(loss_cases):
+    from uaps_b200.losses import ce_loss, dice_loss, uaps_supervised_loss
+    dev = _dev()
+    c = loss_cases["sup_k4c4"]
+    labels = torch.from_numpy(c["labels"]).to(dev)
+    z = [torch.from_numpy(a).to(dev).requires_grad_(True) for a in c["logits"]]
+    sup, tce, tdice, ce_k = uaps_supervised_loss(z, labels)
+    sup.backward()
+    assert sup.item() == pytest.approx(float(c["supervised_loss"]), rel=REL)
+    assert tce.item() == pytest.approx(float(c["total_loss_ce"]), rel=REL)
+    assert tdice.item() == pytest.approx(float(c["total_loss_dice"]), rel=REL)
+    np.testing.assert_allclose(ce_k.cpu().numpy(), c["ce"], rtol=REL)
+    _assert_close(torch.stack([t.grad for t in z]), torch.from_numpy(c["grads"]), "supervised grads")
+    # reference-signature drop-ins, forward and backward
+    for k in range(2):
+        zk = torch.from_numpy(c["logits"][k]).to(dev)
+        a = zk.clone().requires_grad_(True)
+        b = zk.clone().requires_grad_(True)
+        d_ours, d_ref = dice_loss(labels.unsqueeze(1), a), dice_loss_ref(labels.unsqueeze(1), b)
+        assert d_ours.item() == pytest.approx(d_ref.item(), rel=REL)
+        d_ours.backward(); d_ref.backward()
+        _assert_close(a.grad, b.grad, "dice_loss grad")
+        a = zk.clone().requires_grad_(True)
+        b = zk.clone().requires_grad_(True)
+        c_ours, c_ref = ce_loss(a, labels), torch.nn.CrossEntropyLoss()(b, labels)
+        assert c_ours.item() == pytest.approx(c_ref.item(), rel=REL)
+        c_ours.backward(); c_ref.backward()
+        _assert_close(a.grad, b.grad, "ce_loss grad")
+
+
+def test_supervised_against_oracle_on_device():
+    from uaps_b200.losses import uaps_supervised_loss
+    dev = _dev()
+    g = torch.Generator().manual_seed(21)
+    z = [(torch.randn(4, 4, 256, 256, generator=g) * 2).to(dev) for _ in range(4)]
+    labels = torch.randint(0, 4, (4, 256, 256), generator=g).to(dev)
+    zr = [t.clone().requires_grad_(True) for t in z]
+    ref = supervised_loss_ref(zr, labels)
+    ref["supervised_loss"].backward()
+    zs = [t.clone().requires_grad_(True) for t in z]
+    sup, tce, tdice, _ = uaps_supervised_loss(zs, labels)
+    sup.backward()
+    assert sup.item() == pytest.approx(ref["supervised_loss"].item(), rel=REL)
+    assert tce.item() == pytest.approx(ref["total_loss_ce"].item(), rel=REL)
+    assert tdice.item() == pytest.approx(ref["total_loss_dice"].item(), rel=REL)
+    _assert_close(torch.stack([t.grad for t in zs]), torch.stack([t.grad for t in zr]), "grads")
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] upper sizes (1024x1024, large batch): too big for the oracle, so check
+    size-independent properties instead."""
+    from uaps_b200.losses import uaps_unlabeled_loss
+    dev = _dev()
+    K, C, B, H, W = 4, 4, 32, 1024, 1024                    # 33.5 Mpx, 2.1 GB of logits
+    g = torch.Generator(device=dev).manual_seed(5)
+    z = [torch.randn(B, C, H, W, generator=g, device=dev) * 2 for _ in range(K)]
+    mix_w = [0.1, 0.2, 0.3, 0.4]
+    zs = [t.requires_grad_(True) for t in z]
+    loss, ps, unc, pseudo, _ = uaps_unlabeled_loss(zs, mix_w, 0.1, 0.1, return_pseudo=True)
+    loss.backward()
+    # (1) deterministic: a second evaluation reproduces every bit
+    loss2, ps2, unc2, pseudo2, _ = uaps_unlabeled_loss([t.detach() for t in z], mix_w, 0.1, 0.1, return_pseudo=True)
+    assert loss2.item() == loss.item() and torch.equal(pseudo, pseudo2)
+    # (2) softmax-gradient identity: d loss / d z sums to zero over the class axis at every pixel
+    for t in zs:
+        s = t.grad.sum(1)
+        assert s.abs().max().item() <= 1e-5 * t.grad.abs().max().item()
+    # (3) sharding invariance: the loss of the whole batch equals the loss rebuilt from two half-batch
+    #     partial-sum vectors (the N > 1 GPU path) -- checked through the oracle-free identity
+    #     mean over halves of l_uncert == l_uncert
+    h = B // 2
+    _, _, unc_a, pa, _ = uaps_unlabeled_loss([t.detach()[:h] for t in z], mix_w, 0.1, 0.1, return_pseudo=True)
+    _, _, unc_b, pb, _ = uaps_unlabeled_loss([t.detach()[h:] for t in z], mix_w, 0.1, 0.1, return_pseudo=True)
+    assert 0.5 * (unc_a.item() + unc_b.item()) == pytest.approx(unc.item(), rel=1e-6)
+    assert torch.equal(torch.cat([pa, pb]), pseudo)
+    # (4) the pseudo-label is the argmax of the mix on a random subset of pixels (torch CUDA ops)
+    sub = [t.detach()[:1] for t in z]
+    mixed = sum(float(np.float32(w)) * torch.softmax(s, 1) for w, s in zip(mix_w, sub)) if False else None
+    soft = [torch.softmax(s, 1) for s in sub]
+    m = mix_w[0] * soft[0]
+    for k in range(1, K):
+        m = m + mix_w[k] * soft[k]
+    assert torch.equal(torch.argmax(m, 1), pseudo[:1])
+
+
+def test_invalid_arguments_are_rejected():
+    from uaps_b200 import _lib as L
+    from uaps_b200.losses import uaps_unlabeled_loss
+    dev = _dev()
+    z = [torch.randn(1, 4, 8, 8, device=dev) for _ in range(7)]
+    with pytest.raises(RuntimeError):
+        uaps_unlabeled_loss(z, [1 / 7] * 7, 0.1, 0.1)               # K > KMAX
+    z = [torch.randn(1, 9, 8, 8, device=dev) for _ in range(2)]
+    with pytest.raises(RuntimeError):
+        uaps_unlabeled_loss(z, [0.5, 0.5], 0.1, 0.1)                # C > CMAX
+    lib = L.lib()
+    assert lib.uaps_loss_pass1(None, 4, 1, 4, 64, None, None, None, None, None, None, 0, None) == -1

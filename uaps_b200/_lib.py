@@ -1,0 +1,92 @@
+"""ctypes binding of libuaps_b200.so (the C ABI declared in include/uaps_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+Pointers cross the boundary as plain integers (``tensor.data_ptr()``) and the stream as the raw
+``cudaStream_t`` of torch's current stream, so the kernels run in stream order with torch's own
+work and can be captured into CUDA graphs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libuaps_b200.so")
+
+KMAX, CMAX = 6, 8
+LOSS_EXACT = 1
+SC_LOSS_U, SC_PS_LOSS, SC_L_UNCERT, SC_CW1, SC_CW2, SC_INV_N, SC_MEAN_CE, SC_MEAN_DICE, SC_BASE = 0, 1, 2, 3, 4, 5, 6, 7, 8
+
+_vp, _i, _i64, _u64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double
+
+_SIGNATURES = {
+    "uaps_abi_version": (_i, []),
+    "uaps_error_string": (C.c_char_p, [_i]),
+    "uaps_loss_sums_count": (_i, [_i, _i]),
+    "uaps_loss_scalars_count": (_i, [_i, _i]),
+    "uaps_loss_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "uaps_loss_pass1": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "uaps_loss_finalize": (_i, [_vp, _i, _i, _i64, _f, _f, _i, _vp, _vp]),
+    "uaps_loss_pass2": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "uaps_feature_noise": (_i, [_vp, _vp, _u64, _f, _vp, _i, _i64, _vp]),
+    "uaps_dropout": (_i, [_vp, _vp, _u64, _d, _vp, _i64, _vp]),
+    "uaps_fdrop_stats": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp]),
+    "uaps_fdrop_apply": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i64, _vp]),
+    "uaps_perturb3": (_i, [_vp, _vp, _vp, _u64, _f, _d, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i64, _vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def exported_symbols() -> Sequence[str]:
+    return tuple(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly if it was never built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m uaps_b200.build` "
+                "(or __graft_entry__.build()).  uaps_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the ABI and the binding diverge
+            fn.restype, fn.argtypes = res, args
+        if handle.uaps_abi_version() != 1:
+            raise RuntimeError("libuaps_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().uaps_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    """Host array of device pointers (``const float* const*``)."""
+    arr = (_vp * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def float_array(vals: Sequence[float]):
+    return (C.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("uaps_b200 kernels run on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
