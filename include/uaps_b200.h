@@ -149,6 +149,13 @@ int uaps_perturb3(const float* x, const float* noise, const uint8_t* keep, uint6
                   float* y_noise, float* y_drop, float* y_fdrop,
                   int B, int C, int64_t HW, cudaStream_t stream);
 
+/* Backward of uaps_perturb3: dx = g_noise*n + g_noise + g_drop*keep/(1-p) + g_fdrop*mask, one pass.
+ * Any of the three upstream gradients may be NULL (that branch had no consumer). */
+int uaps_perturb3_bwd(const float* g_noise, const float* g_drop, const float* g_fdrop,
+                      const float* noise, const uint8_t* keep, uint64_t seed, float noise_range,
+                      double p_drop, const float* attention, const uint32_t* smax_enc, float u,
+                      float* dx, int B, int C, int64_t HW, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,8 +80,12 @@ def test_against_oracle_on_device(K, C, B, H, W, scale, exact):
     o = _ours(z, mix_w, cw1, cw2, exact)
     assert torch.equal(o["pseudo"], ref["pseudo"]), \
         f"pseudo-label mismatches: {(o['pseudo'] != ref['pseudo']).sum().item()} of {ref['pseudo'].numel()}"
+    # 1e-5 relative.  In the default (MUFU) arithmetic l_uncert additionally gets an absolute floor of
+    # 3e-8: it is a mean of differences of O(1) log terms, and when the decoders agree (V ~ 1e-3) a
+    # quarter-ulp systematic error of those terms is already > 1e-5 of the mean.  UAPS_LOSS_EXACT has no floor.
+    floor = {"l_uncert": 0.0 if exact else 3e-8, "loss_u": 0.0 if exact else 3e-9, "ps_loss": 0.0}
     for key in ("loss_u", "ps_loss", "l_uncert"):
-        assert o[key].item() == pytest.approx(ref[key].item(), rel=REL), key
+        assert o[key].item() == pytest.approx(ref[key].item(), rel=REL, abs=floor[key]), key
     _assert_close(torch.stack(o["exp_var"]), torch.stack(ref["exp_var"]), "exp_var")
     _assert_close(torch.stack(o["grads"]), torch.stack([t.grad for t in zr]), "grads")
     # and the fp64 closed form, independent of autograd

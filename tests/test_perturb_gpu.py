@@ -1,0 +1,105 @@
+"""GPU parity of the perturbation kernels (UAPS_unet.py:156-185) through the C ABI: golden vectors made
+from the reference's own functions, oracle on device, Philox-mode statistical and replay properties."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle.perturb_ref import dropout_ref, feature_dropout_ref, feature_noise_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _g():
+    return {k: v for k, v in np.load(os.path.join(GOLDEN, "perturb.npz")).items()}
+
+
+def test_golden_injected():
+    from uaps_b200 import perturb as P
+    dev = torch.device("cuda:0")
+    g = _g()
+    x = torch.from_numpy(g["x"]).to(dev)
+    noise, keep, u = torch.from_numpy(g["noise"]).to(dev), torch.from_numpy(g["keep"]).to(dev), float(g["u"])
+    assert torch.equal(P.FeatureNoise()(x, noise=noise).cpu(), torch.from_numpy(g["y_noise"]))
+    assert torch.equal(P.Dropout(x, 0.5, keep=keep).cpu(), torch.from_numpy(g["y_drop"]))
+    assert torch.equal(P.FeatureDropout(x, u=u).cpu(), torch.from_numpy(g["y_fd"]))
+    yn, yd, yf = P.perturb3(x, noise=noise, keep=keep, u=u)
+    assert torch.equal(yn.cpu(), torch.from_numpy(g["y_noise"]))
+    assert torch.equal(yd.cpu(), torch.from_numpy(g["y_drop"]))
+    assert torch.equal(yf.cpu(), torch.from_numpy(g["y_fd"]))
+
+
+@pytest.mark.parametrize("shape", [(4, 16, 256, 256), (2, 256, 16, 16), (3, 32, 25, 29), (2, 64, 58, 160)])
+def test_against_oracle_with_gradients(shape):
+    from uaps_b200 import perturb as P
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=gen).to(dev)
+    noise = ((torch.rand(shape[1:], generator=gen) * 2 - 1) * 0.3).to(dev)
+    keep = (torch.rand(shape, generator=gen) >= 0.5).to(dev)
+    u = 0.8123
+    cots = [torch.randn(shape, generator=gen).to(dev) for _ in range(3)]
+
+    xr = x.clone().requires_grad_(True)
+    refs = [feature_noise_ref(xr, noise), dropout_ref(xr, keep, 0.5), feature_dropout_ref(xr, u)]
+    sum((r * c).sum() for r, c in zip(refs, cots)).backward()
+
+    xo = x.clone().requires_grad_(True)
+    outs = P.perturb3(xo, noise=noise, keep=keep, u=u)
+    sum((o * c).sum() for o, c in zip(outs, cots)).backward()
+    assert torch.equal(outs[0], refs[0]) and torch.equal(outs[1], refs[1])
+    # the drop mask compares a channel-mean against a threshold: summation order may flip a pixel that
+    # sits within an ulp of it; allow at most a handful of such pixels
+    bad = (outs[2] != refs[2]).flatten(2).any(1).sum().item() if outs[2].dim() == 4 else 0
+    assert bad <= 2, bad
+    if bad == 0:
+        assert torch.allclose(xo.grad, xr.grad, rtol=1e-6, atol=1e-6)
+
+    # separate entry points too
+    xs = x.clone().requires_grad_(True)
+    ys = [P.FeatureNoise()(xs, noise=noise), P.Dropout(xs, 0.5, keep=keep), P.FeatureDropout(xs, u=u)]
+    sum((o * c).sum() for o, c in zip(ys, cots)).backward()
+    assert torch.equal(ys[0], refs[0]) and torch.equal(ys[1], refs[1])
+    if bad == 0:
+        assert torch.equal(ys[2], refs[2])
+        assert torch.allclose(xs.grad, xr.grad, rtol=1e-6, atol=1e-6)
+
+
+def test_encoder_dropout_rates():
+    """nn.Dropout(p) of the encoder blocks (:40), p = 0.05 .. 0.5, injected masks vs torch."""
+    from uaps_b200 import perturb as P
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 16, 64, 64, generator=gen).to(dev)
+    for p in (0.05, 0.1, 0.2, 0.3, 0.5):
+        keep = (torch.rand(x.shape, generator=gen) >= p).to(dev)
+        ref = dropout_ref(x, keep, p)
+        out = P.Dropout(x, p, keep=keep)
+        assert torch.allclose(out, ref, rtol=2e-7, atol=0)
+
+
+def test_philox_mode_statistics_and_replay():
+    from uaps_b200 import perturb as P
+    dev = torch.device("cuda:0")
+    x = torch.ones(8, 32, 64, 64, device=dev, requires_grad=True)
+    yn, yd, yf = P.perturb3(x, seed=1234, u=0.8)
+    n = yn.detach() - 1.0                                   # x = 1 -> y = 1 + noise
+    assert torch.equal(n[0], n[5])                          # one draw shared by the batch
+    assert n.abs().max().item() <= 0.3 and abs(n.mean().item()) < 5e-3
+    assert n.std().item() == pytest.approx(0.3 / 3 ** 0.5, rel=0.02)
+    frac = (yd.detach() != 0).float().mean().item()
+    assert frac == pytest.approx(0.5, abs=5e-3)
+    assert set(yd.detach().unique().tolist()) <= {0.0, 2.0}
+    assert not torch.equal(yd.detach()[0], yd.detach()[1])  # dropout differs per sample
+    # backward regenerates the same draw from the seed (no stored mask)
+    (yn.sum() + yd.sum()).backward()
+    assert torch.allclose(x.grad, (1.0 + n) + yd.detach(), rtol=1e-6, atol=1e-6)
+    # same seed -> same draw; other seed -> other draw
+    yn2, yd2, _ = P.perturb3(x.detach(), seed=1234, u=0.8)
+    yn3, _, _ = P.perturb3(x.detach(), seed=99, u=0.8)
+    assert torch.equal(yn2, yn.detach()) and torch.equal(yd2, yd.detach()) and not torch.equal(yn3, yn2)
+    # stand-alone entry points draw the same stream as the fused kernel
+    assert torch.equal(P.FeatureNoise()(x.detach(), seed=1234), yn.detach())
+    assert torch.equal(P.Dropout(x.detach(), 0.5, seed=1234), yd.detach())

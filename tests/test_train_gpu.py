@@ -1,0 +1,58 @@
+"""GPU: one full UAPS iteration through UAPSTrainer against the oracle's iteration (functional U-Net +
+restated losses + autograd + Adam) with every random draw injected."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.unet_ref import feature_shapes, synthetic_rand, synthetic_state_dict, unet_uaps_ref
+from oracle.uaps_loss_ref import consistency_weight_ref, supervised_loss_ref, unlabeled_loss_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def test_training_iteration_matches_oracle():
+    from uaps_b200.train import UAPSTrainer
+    from uaps_b200.unet import UNet_UAPS
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, C = 2, 64, 64, 4
+    sd = synthetic_state_dict(3, C, seed=11)
+    model = UNet_UAPS(3, C)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    trainer = UAPSTrainer(model)
+    trainer.iter_num = 8000                                   # mid-ramp: cw = 0.1 * exp(-5 (1 - 100/200)^2)
+    g = torch.Generator().manual_seed(2)
+    xl, xu = torch.randn(B, 3, H, W, generator=g).to(dev), torch.randn(B, 3, H, W, generator=g).to(dev)
+    yl = torch.randint(0, C, (B, H, W), generator=g).to(dev)
+    to = lambda r: {k: [v.to(dev) if torch.is_tensor(v) else v for v in vals] for k, vals in r.items()}
+    rl, ru = to(synthetic_rand(feature_shapes(B, H, W), 1)), to(synthetic_rand(feature_shapes(B, H, W), 2))
+    mix_w = np.random.default_rng(3).dirichlet(np.ones(4))
+
+    # oracle iteration on the same device
+    params = {k: v.to(dev).clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    full = {**{k: v.to(dev) for k, v in sd.items()}, **params}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
+    ol, ou = unet_uaps_ref(xl, full, rl)[:4], unet_uaps_ref(xu, full, ru)[:4]
+    cw = consistency_weight_ref(8000)
+    ref_sup = supervised_loss_ref(ol, yl)
+    ref_un = unlabeled_loss_ref(ou, mix_w, cw, cw)
+    ref_loss = ref_sup["supervised_loss"] + ref_un["loss_u"]
+    opt.zero_grad(); ref_loss.backward(); opt.step()
+
+    out = trainer.step(xl, yl, xu, mix_w=mix_w, rand_l=rl, rand_u=ru)
+    assert trainer.consistency_weights()[0] == pytest.approx(consistency_weight_ref(8001), rel=1e-12)
+    assert out["loss"].item() == pytest.approx(ref_loss.item(), rel=2e-4)
+    assert out["supervised_loss"].item() == pytest.approx(ref_sup["supervised_loss"].item(), rel=2e-4)
+    assert out["ps_loss"].item() == pytest.approx(ref_un["ps_loss"].item(), rel=2e-4)
+    assert out["l_uncert"].item() == pytest.approx(ref_un["l_uncert"].item(), rel=2e-3)
+    # parameters after one Adam step: Adam normalises the gradient, so compare the update direction
+    new = dict(model.named_parameters())
+    agree, total = 0, 0
+    for k, p_ref in params.items():
+        if k.endswith(("conv_conv.0.bias", "conv_conv.4.bias")):
+            continue                                          # analytically zero gradient in front of train-mode BN
+        d_ref, d_new = (p_ref.detach() - sd[k].to(dev)), (new[k].detach() - sd[k].to(dev))
+        agree += (torch.sign(d_ref) == torch.sign(d_new)).sum().item()
+        total += d_ref.numel()
+    assert agree / total > 0.995, agree / total

@@ -83,7 +83,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kTieMargin = 2e-5f;
 
-template <int C>
+// PLOG: take log(s) with the precise logf.  Pass 1 sets it: the batch means of V_k (differences of
+// logs, ~1e-3 when the decoders agree) must not inherit the mantissa-dependent bias of lg2.approx.
+template <int C, bool PLOG>
 __device__ __forceinline__ void softmax_fast(const float (&z)[C], float (&p)[C], float (&l)[C]) {
     float m = z[0];
 #pragma unroll
@@ -97,7 +99,7 @@ __device__ __forceinline__ void softmax_fast(const float (&z)[C], float (&p)[C],
         s += e[c];
     }
     const float r = rcp_approx(s);
-    const float nls = -lg2_approx(s) * kLn2;
+    const float nls = PLOG ? -logf(s) : -lg2_approx(s) * kLn2;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         p[c] = e[c] * r;
@@ -129,13 +131,13 @@ __device__ __noinline__ int argmax_exact_from_logits(const float (&z)[K][C], con
     return argmax_exact<K, C>(p, w);
 }
 
-template <int K, int C, bool SUP, bool EXACT>
+template <int K, int C, bool SUP, bool EXACT, bool PLOG>
 __device__ __forceinline__ void pixel_forward(const float (&z)[K][C], const float (&w)[K], int label,
                                               PixelState<K, C>& st) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if constexpr (EXACT) softmax_exact<C>(z[k], st.p[k], st.l[k]);
-        else softmax_fast<C>(z[k], st.p[k], st.l[k]);
+        else softmax_fast<C, PLOG>(z[k], st.p[k], st.l[k]);
     }
     if constexpr (SUP) {
         st.y = label;
@@ -169,7 +171,7 @@ __device__ __forceinline__ void pixel_forward(const float (&z)[K][C], const floa
             for (int k = 1; k < K; ++k) acc = __fadd_rn(acc, st.p[k][c]);
             const float q = acc * (1.0f / K);
             st.q[c] = q;
-            st.lq[c] = EXACT ? logf(q) : lg2_approx(q) * kLn2;
+            st.lq[c] = (EXACT || PLOG) ? logf(q) : lg2_approx(q) * kLn2;
             h += (q == 0.f) ? 0.f : q * st.lq[c];
         }
 #pragma unroll
@@ -183,6 +185,18 @@ __device__ __forceinline__ void pixel_forward(const float (&z)[K][C], const floa
     }
 }
 
+// K*C independent vector loads of one pixel group (one per class plane of every decoder)
+template <int K, int C, int VEC>
+__device__ __forceinline__ void load_group(const LossArgs& a, unsigned g, float (&zv)[K][C][VEC]) {
+    const unsigned b = g / a.groups_per_image;
+    const unsigned hw = (g - b * a.groups_per_image) * VEC;
+    const size_t base = (size_t)b * C * a.HW + hw;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int c = 0; c < C; ++c) load_vec<VEC>(a.z[k] + base + (size_t)c * a.HW, zv[k][c]);
+}
+
 // ---- pass 1 --------------------------------------------------------------------------------
 // running sums of one thread, flat in the order of `sums` (see uaps_loss_sums_count); every index
 // below is a compile-time constant after unrolling, so the array lives in registers
@@ -193,7 +207,7 @@ struct AccIdx {
 };
 
 template <int K, int C, int VEC, bool SUP, bool EXACT>
-__global__ void __launch_bounds__(LOSS_THREADS)
+__global__ void __launch_bounds__(LOSS_THREADS, 1)
 loss_pass1_kernel(const LossArgs a, unsigned* __restrict__ ticket, float* __restrict__ partials,
                   double* __restrict__ sums) {
     constexpr int S = sums_count(K, C);
@@ -209,8 +223,13 @@ loss_pass1_kernel(const LossArgs a, unsigned* __restrict__ ticket, float* __rest
 #pragma unroll
     for (int i = 0; i < S; ++i) acc[i] = 0.f;
 
+    // register double buffering: the next group's K*C loads are in flight while this one is computed
+    // (the kernel runs at one CTA per SM, so latency is hidden by prefetch depth, not occupancy)
     const unsigned stride = gridDim.x * LOSS_THREADS;
-    for (unsigned g = blockIdx.x * LOSS_THREADS + threadIdx.x; g < a.ngroups; g += stride) {
+    unsigned g = blockIdx.x * LOSS_THREADS + threadIdx.x;
+    float zn[K][C][VEC];
+    if (g < a.ngroups) load_group<K, C, VEC>(a, g, zn);
+    for (; g < a.ngroups; g += stride) {
         const unsigned b = g / a.groups_per_image;
         const unsigned hw = (g - b * a.groups_per_image) * VEC;
         const size_t base = (size_t)b * C * a.HW + hw;
@@ -218,7 +237,10 @@ loss_pass1_kernel(const LossArgs a, unsigned* __restrict__ ticket, float* __rest
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int c = 0; c < C; ++c) load_vec<VEC>(a.z[k] + base + (size_t)c * a.HW, zv[k][c]);
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) zv[k][c][j] = zn[k][c][j];
+        if (g + stride < a.ngroups) load_group<K, C, VEC>(a, g + stride, zn);
         long long lab[VEC];
         if constexpr (SUP) {
 #pragma unroll
@@ -234,7 +256,7 @@ loss_pass1_kernel(const LossArgs a, unsigned* __restrict__ ticket, float* __rest
 #pragma unroll
                 for (int c = 0; c < C; ++c) z[k][c] = zv[k][c][j];
             PixelState<K, C> st;
-            pixel_forward<K, C, SUP, EXACT>(z, w, SUP ? (int)lab[j] : 0, st);
+            pixel_forward<K, C, SUP, EXACT, true>(z, w, SUP ? (int)lab[j] : 0, st);
             yv[j] = st.y;
             // one-hot of the label as arithmetic masks (keeps p/l in registers: no select chains
             // that the compiler would turn into a local-memory indexed load)
@@ -365,7 +387,7 @@ struct GradConsts {
 };
 
 template <int K, int C, int VEC, bool SUP, bool EXACT>
-__global__ void __launch_bounds__(LOSS_THREADS)
+__global__ void __launch_bounds__(LOSS_THREADS, 1)
 loss_pass2_kernel(const LossArgs a, const float* __restrict__ sc, const float* __restrict__ grad_out) {
     __shared__ GradConsts<K, C> gc;
     if (threadIdx.x == 0) {
@@ -399,8 +421,13 @@ loss_pass2_kernel(const LossArgs a, const float* __restrict__ sc, const float* _
 #pragma unroll
     for (int k = 0; k < K; ++k) w[k] = a.w[k];
 
+    // register double buffering: the next group's K*C loads are in flight while this one is computed
+    // (the kernel runs at one CTA per SM, so latency is hidden by prefetch depth, not occupancy)
     const unsigned stride = gridDim.x * LOSS_THREADS;
-    for (unsigned g = blockIdx.x * LOSS_THREADS + threadIdx.x; g < a.ngroups; g += stride) {
+    unsigned g = blockIdx.x * LOSS_THREADS + threadIdx.x;
+    float zn[K][C][VEC];
+    if (g < a.ngroups) load_group<K, C, VEC>(a, g, zn);
+    for (; g < a.ngroups; g += stride) {
         const unsigned b = g / a.groups_per_image;
         const unsigned hw = (g - b * a.groups_per_image) * VEC;
         const size_t base = (size_t)b * C * a.HW + hw;
@@ -408,7 +435,10 @@ loss_pass2_kernel(const LossArgs a, const float* __restrict__ sc, const float* _
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int c = 0; c < C; ++c) load_vec<VEC>(a.z[k] + base + (size_t)c * a.HW, zv[k][c]);
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) zv[k][c][j] = zn[k][c][j];
+        if (g + stride < a.ngroups) load_group<K, C, VEC>(a, g + stride, zn);
         long long lab[VEC];
         if constexpr (SUP) {
 #pragma unroll
@@ -422,7 +452,7 @@ loss_pass2_kernel(const LossArgs a, const float* __restrict__ sc, const float* _
 #pragma unroll
                 for (int c = 0; c < C; ++c) z[k][c] = zv[k][c][j];
             PixelState<K, C> st;
-            pixel_forward<K, C, SUP, EXACT>(z, w, SUP ? (int)lab[j] : 0, st);
+            pixel_forward<K, C, SUP, EXACT, false>(z, w, SUP ? (int)lab[j] : 0, st);
 
             float gk[K];
             float Gq[C];

@@ -305,3 +305,96 @@ UAPS_API int uaps_perturb3(const float* x, const float* noise, const uint8_t* ke
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
+
+// Backward of uaps_perturb3: the three upstream gradients are read once and folded into one
+// dx = g_noise * n + g_noise  +  g_drop * keep / (1 - p)  +  g_fdrop * mask   (any g_* may be NULL).
+namespace uaps {
+namespace {
+template <int VEC>
+__global__ void __launch_bounds__(PT) perturb3_bwd_kernel(const float* __restrict__ g_noise, const float* __restrict__ g_drop,
+                                                          const float* __restrict__ g_fdrop, const float* __restrict__ noise,
+                                                          const uint8_t* __restrict__ keep, uint64_t seed, float range,
+                                                          float p, float scale, const float* __restrict__ attention,
+                                                          const uint32_t* __restrict__ smax_enc, float u,
+                                                          float* __restrict__ dx, int C, long long HW) {
+    const int b = blockIdx.y;
+    const long long chw = (long long)C * HW;
+    const size_t off = (size_t)b * chw;
+    const float thr = (g_fdrop != nullptr) ? __fmul_rn(dec_ordered(smax_enc[b]), u) : 0.f;
+    const long long nv = HW / VEC;
+    for (long long v = (long long)blockIdx.x * PT + threadIdx.x; v < nv; v += (long long)gridDim.x * PT) {
+        float m[VEC];
+        if (g_fdrop != nullptr) {
+            float a[VEC];
+            load_vec<VEC>(attention + (size_t)b * HW + v * VEC, a);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) m[i] = (a[i] < thr) ? 1.f : 0.f;
+        }
+#pragma unroll 2
+        for (int c = 0; c < C; ++c) {
+            const long long e = (long long)c * HW + v * VEC;
+            float o[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+            if (g_noise != nullptr) {
+                float gv[VEC], n[VEC];
+                load_vec<VEC>(g_noise + off + e, gv);
+                if (noise != nullptr) load_vec<VEC>(noise + e, n);
+                else {
+                    float n4[4];
+                    philox_noise4(seed, (uint64_t)e / 4, range, n4);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) n[i] = n4[(e + i) & 3];
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o[i] = __fadd_rn(__fmul_rn(gv[i], n[i]), gv[i]);
+            }
+            if (g_drop != nullptr) {
+                float gv[VEC], k[VEC];
+                load_vec<VEC>(g_drop + off + e, gv);
+                if (keep != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) k[i] = keep[off + e + i] ? 1.f : 0.f;
+                } else {
+                    float k4[4];
+                    philox_keep4(seed, (uint64_t)(off + e) / 4, p, k4);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) k[i] = k4[(off + e + i) & 3];
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o[i] += gv[i] * k[i] * scale;
+            }
+            if (g_fdrop != nullptr) {
+                float gv[VEC];
+                load_vec<VEC>(g_fdrop + off + e, gv);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o[i] += gv[i] * m[i];
+            }
+            store_vec<VEC>(dx + off + e, o);
+        }
+    }
+}
+}  // namespace
+}  // namespace uaps
+
+UAPS_API int uaps_perturb3_bwd(const float* g_noise, const float* g_drop, const float* g_fdrop, const float* noise,
+                               const uint8_t* keep, uint64_t seed, float noise_range, double p_drop,
+                               const float* attention, const uint32_t* smax_enc, float u, float* dx, int B, int C,
+                               int64_t HW, cudaStream_t stream) {
+    if (dx == nullptr || B <= 0 || C <= 0 || HW <= 0) return UAPS_EINVAL;
+    if (g_noise == nullptr && g_drop == nullptr && g_fdrop == nullptr) return UAPS_EINVAL;
+    if (g_fdrop != nullptr && (attention == nullptr || smax_enc == nullptr)) return UAPS_EINVAL;
+    if (B > 65535 || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
+    const float scale = keep_scale(p_drop);
+    const int vec = vec_for(HW, {g_noise, g_drop, g_fdrop, noise, attention, dx});
+    if (vec == 4)
+        perturb3_bwd_kernel<4><<<grid_hw_b(HW / 4, B), PT, 0, stream>>>(g_noise, g_drop, g_fdrop, noise, keep, seed,
+                                                                       noise_range, (float)p_drop, scale, attention,
+                                                                       smax_enc, u, dx, C, HW);
+    else
+        perturb3_bwd_kernel<1><<<grid_hw_b(HW, B), PT, 0, stream>>>(g_noise, g_drop, g_fdrop, noise, keep, seed,
+                                                                   noise_range, (float)p_drop, scale, attention,
+                                                                   smax_enc, u, dx, C, HW);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}

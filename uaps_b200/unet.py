@@ -1,0 +1,152 @@
+"""Drop-in UAPS multi-decoder U-Net (utilities/UAPS_unet.py:208-233) on the B200 kernels.
+
+``UNet_UAPS(in_chns, class_num)`` keeps the reference's constructor, its 4-tuple output
+``(main, aux1, aux2, aux3)`` of [B, C, H, W] fp32 logits, and -- key for key, 334 tensors -- its
+``state_dict`` (e.g. ``encoder.down2.maxpool_conv.1.conv_conv.4.weight``,
+``aux_decoder3.up1.conv1x1.bias``), so reference checkpoints load unchanged (with or without the
+``module.`` prefix DataParallel adds, see ``load_reference_state_dict``).
+
+Internally it is not a module-per-layer tree: parameters sit in holder modules that only give
+them their reference names, and ``forward`` is a straight-line program.  The three auxiliary
+perturbations of all five encoder levels (reference :227-231: 15 tensors, ~40 ATen launches, a CPU
+RNG draw plus an H2D copy per level) are one fused kernel per level (``perturb.perturb3``), the
+encoder-block dropout (:40) is the Philox dropout kernel.
+
+Layer semantics kept from the reference: the up path is conv1x1 +
+bilinear(align_corners=True) because ``UpBlock``'s ``bilinear=True`` default wins (:69);
+``F.dropout`` of aux2 is active in eval mode too (:156-158); H and W must be multiples of 16.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import perturb as P
+
+FT_CHNS = (16, 32, 64, 128, 256)            # UAPS_unet.py:212
+ENC_DROPOUT = (0.05, 0.1, 0.2, 0.3, 0.5)    # :214
+_AUX_KINDS = ("noise", "dropout", "fdrop")  # :227, :229, :231; a 4th/5th aux decoder re-uses them in order
+
+
+def _holder(**children: nn.Module) -> nn.Module:
+    m = nn.Module()
+    for name, child in children.items():
+        m.add_module(name, child)
+    return m
+
+
+def _conv_block(cin: int, cout: int) -> nn.Module:
+    """Parameters of ConvBlock (:31-47) under its Sequential indices 0 (conv), 1 (BN), 4 (conv), 5 (BN)."""
+    return _holder(conv_conv=_holder(**{
+        "0": nn.Conv2d(cin, cout, kernel_size=3, padding=1), "1": nn.BatchNorm2d(cout),
+        "4": nn.Conv2d(cout, cout, kernel_size=3, padding=1), "5": nn.BatchNorm2d(cout)}))
+
+
+def _encoder(in_chns: int) -> nn.Module:
+    enc = _holder(in_conv=_conv_block(in_chns, FT_CHNS[0]))
+    for lvl in range(1, 5):                                   # DownBlock (:50-62): MaxPool2d is child "0", block is "1"
+        enc.add_module(f"down{lvl}", _holder(maxpool_conv=_holder(**{"1": _conv_block(FT_CHNS[lvl - 1], FT_CHNS[lvl])})))
+    return enc
+
+
+def _decoder(class_num: int) -> nn.Module:
+    dec = nn.Module()
+    for i in range(1, 5):                                     # UpBlock (:65-86), channels :129-136
+        c1, c2 = FT_CHNS[5 - i], FT_CHNS[4 - i]
+        dec.add_module(f"up{i}", _holder(conv1x1=nn.Conv2d(c1, c2, kernel_size=1), conv=_conv_block(2 * c2, c2)))
+    dec.add_module("out_conv", nn.Conv2d(FT_CHNS[0], class_num, kernel_size=3, padding=1))
+    return dec
+
+
+class UNet_UAPS(nn.Module):
+    def __init__(self, in_chns: int, class_num: int, n_aux: int = 3):
+        super().__init__()
+        if not 0 <= n_aux <= 5:
+            raise ValueError("n_aux must be in [0, 5]")
+        self.in_chns, self.class_num, self.n_aux = in_chns, class_num, n_aux
+        self.encoder = _encoder(in_chns)
+        self.main_decoder = _decoder(class_num)
+        for a in range(1, n_aux + 1):
+            self.add_module(f"aux_decoder{a}", _decoder(class_num))
+
+    # ---- layers -----------------------------------------------------------------------------
+    def _block(self, x: torch.Tensor, blk: nn.Module, p_drop: float, keep, seed) -> torch.Tensor:
+        cc = blk.conv_conv
+        y = F.leaky_relu(cc.get_submodule("1")(cc.get_submodule("0")(x)), 0.01)
+        if p_drop > 0.0 and self.training:                    # nn.Dropout(p) between the two convs (:40)
+            y = P.Dropout(y, p_drop, keep=keep, seed=seed)
+        return F.leaky_relu(cc.get_submodule("5")(cc.get_submodule("4")(y)), 0.01)
+
+    def encode(self, x: torch.Tensor, enc_keep: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """Encoder.forward (:110-116): five levels, MaxPool2d(2) in front of levels 1-4."""
+        feats = []
+        for lvl in range(5):
+            if lvl == 0:
+                blk = self.encoder.in_conv
+            else:
+                x = F.max_pool2d(x, 2)
+                blk = self.encoder.get_submodule(f"down{lvl}").maxpool_conv.get_submodule("1")
+            x = self._block(x, blk, ENC_DROPOUT[lvl], None if enc_keep is None else enc_keep[lvl], None)
+            feats.append(x)
+        return feats
+
+    def decode(self, feats: Sequence[torch.Tensor], dec: nn.Module) -> torch.Tensor:
+        """Decoder.forward (:141-153) with UpBlock.forward (:81-86)."""
+        x = feats[4]
+        for i in range(1, 5):
+            up = dec.get_submodule(f"up{i}")
+            x = up.conv1x1(x)
+            x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+            x = torch.cat([feats[4 - i], x], dim=1)
+            x = self._block(x, up.conv, 0.0, None, None)
+        return dec.out_conv(x)
+
+    def decoders(self) -> List[nn.Module]:
+        return [self.main_decoder] + [self.get_submodule(f"aux_decoder{a}") for a in range(1, self.n_aux + 1)]
+
+    # ---- forward ----------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, rand: Optional[Dict[str, list]] = None):
+        """UNet_UAPS.forward (:224-233).  ``rand`` optionally injects every random draw:
+        {"enc_keep": 5 masks, "noise": 5 tensors [C_l,H_l,W_l], "aux2_keep": 5 masks, "u": 5 floats}."""
+        if x.shape[-1] % 16 or x.shape[-2] % 16:
+            raise RuntimeError("H and W must be multiples of 16 (four 2x poolings; the reference fails in torch.cat)")
+        feats = self.encode(x, None if rand is None else rand["enc_keep"])
+        outs = [self.decode(feats, self.main_decoder)]
+        if self.n_aux == 0:
+            return outs[0]
+        per_kind: Dict[str, List[torch.Tensor]] = {k: [] for k in _AUX_KINDS}
+        for lvl, f in enumerate(feats):
+            kw = {} if rand is None else {"noise": rand["noise"][lvl], "keep": rand["aux2_keep"][lvl], "u": rand["u"][lvl]}
+            yn, yd, yf = P.perturb3(f, **kw)
+            per_kind["noise"].append(yn); per_kind["dropout"].append(yd); per_kind["fdrop"].append(yf)
+        for a in range(1, self.n_aux + 1):
+            kind = _AUX_KINDS[(a - 1) % 3]
+            if a <= 3:
+                pf = per_kind[kind]
+            elif kind == "noise":                              # aux4+: a fresh draw of the same perturbation family
+                pf = [P.FeatureNoise()(f) for f in feats]
+            elif kind == "dropout":
+                pf = [P.Dropout(f) for f in feats]
+            else:
+                pf = [P.FeatureDropout(f) for f in feats]
+            outs.append(self.decode(pf, self.get_submodule(f"aux_decoder{a}")))
+        return tuple(outs)
+
+
+def load_reference_state_dict(model: nn.Module, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+    """Load a reference checkpoint's ``state_dict`` (UAPS_train.py:443-450), with or without the
+    ``module.`` prefix that ``nn.DataParallel`` (UAPS_model.py:13) puts on every key."""
+    cleaned = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+    return model.load_state_dict(cleaned, strict=strict)
+
+
+def net_factory(net_type: str = "unet_uaps", in_chns: int = 3, class_num: int = 4):
+    """utilities/UAPS_net_factory.py:5-13: the model on CUDA, or None for an unknown type."""
+    if net_type == "unet_uaps":
+        return UNet_UAPS(in_chns=in_chns, class_num=class_num).cuda()
+    if net_type == "unet":
+        return UNet_UAPS(in_chns=in_chns, class_num=class_num, n_aux=0).cuda()
+    return None
