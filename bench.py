@@ -276,6 +276,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, t1, t2, tmid = t.tolist()
 
+    # secondary shape (DAGM-sized images): same kernels, 4x the pixels per launch
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = loss_sweep(dev, lib, L)
+
     train = None
     if not args.no_train_step:
         try:
@@ -317,11 +322,47 @@ def run_ours(args):
             pxs, sec = cpu_baseline(5, 1, threads)
             line["cpu_baseline"] = {"value": pxs, "unit": "pixels/s", "cores": threads, "kind": "port",
                                     "sample": f"oracle (reference expressions, torch CPU) fwd+bwd, 5 steps of {CPU_SAMPLE_B}x{H}x{W} px"}
+        if sweep is not None:
+            line["sweep"] = sweep
         if train is not None:
             line["train_step"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def loss_sweep(dev, lib, L, iters: int = 10):
+    """Other points of BASELINE configs[1]'s sweep, device-resident, same timing method as the headline."""
+    peak, _ = measured_hbm_peak()
+    out = []
+    for (k, c, b, h, w) in [(4, 4, 64, 512, 512), (4, 2, 32, 512, 512), (5, 2, 32, 256, 512), (6, 4, 32, 512, 512),
+                            (4, 4, 8, 200, 200)]:
+        z = [torch.randn(b, c, h, w, device=dev) * 2 for _ in range(k)]
+        dz = [torch.empty_like(t) for t in z]
+        ws = torch.zeros(lib.uaps_loss_workspace_bytes(k, c), dtype=torch.uint8, device=dev)
+        sums = torch.empty(lib.uaps_loss_sums_count(k, c), dtype=torch.float64, device=dev)
+        sc = torch.empty(lib.uaps_loss_scalars_count(k, c), dtype=torch.float32, device=dev)
+        go = torch.zeros_like(sc); go[0] = 1.0
+        zp, dzp, wa, st = L.ptr_array(z), L.ptr_array(dz), L.float_array([1.0 / k] * k), L.stream_ptr()
+        n = b * h * w
+
+        def step():
+            L.check(lib.uaps_loss_pass1(zp, k, b, c, h * w, wa, None, ws.data_ptr(), sums.data_ptr(), None, None, 0, st), "p1")
+            L.check(lib.uaps_loss_finalize(sums.data_ptr(), k, c, n, CW1, CW2, 0, sc.data_ptr(), st), "fin")
+            L.check(lib.uaps_loss_pass2(zp, k, b, c, h * w, wa, None, sc.data_ptr(), go.data_ptr(), dzp, 0, st), "p2")
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out.append({"K": k, "C": c, "B": b, "H": h, "W": w, "ms_per_step": ms, "pixels_per_s": n / (ms * 1e-3),
+                    "fwd_bwd_frac_of_hbm_peak": 12 * k * c * n / (ms * 1e-3) / 1e9 / peak})
+        del z, dz
+    return out
 
 
 def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3):
@@ -372,6 +413,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -2,15 +2,14 @@
 // fused_loss_k*.cu).  Host side only validates, packs the by-value kernel argument block and picks
 // the vector width; it never allocates, synchronises or retains pointers.
 #define UAPS_LOSS_ENTRY
+#include <cstdlib>
 #include "fused_loss_impl.cuh"
 
 namespace uaps {
 namespace loss {
-#define UAPS_DECL_K(KK)                                                                                   \
-    extern template int launch_pass1_k<KK>(int, int, bool, bool, const LossArgs&, unsigned*, float*, double*,   \
-                                           cudaStream_t);                                                 \
-    extern template int launch_pass2_k<KK>(int, int, bool, bool, const LossArgs&, const float*, const float*,   \
-                                           cudaStream_t);
+#define UAPS_DECL_K(KK)                                                                                       \
+    extern template int launch_loss_k<KK>(int, int, bool, bool, const LossArgs&, float*, const float*,       \
+                                          const float*, int*, cudaStream_t);
 UAPS_DECL_K(1) UAPS_DECL_K(2) UAPS_DECL_K(3) UAPS_DECL_K(4) UAPS_DECL_K(5) UAPS_DECL_K(6)
 #undef UAPS_DECL_K
 }  // namespace loss
@@ -44,10 +43,29 @@ int pick_vec(const float* const* z, float* const* o, int K, int64_t HW) {
 }
 
 
-// vector width actually used: the widest the (K,C) instantiation has, if shape/alignment allow it
-int final_vec(int K, int C, int avail) {
-    const int vm = max_vec(K, C);
-    return (avail >= vm && vm > 1) ? vm : 1;
+// Kernel variant for a call: pass 1 runs 4 pixels/thread, pass 2 two (both software-pipelined) when
+// the planes are 16-byte aligned (HW % 4 == 0); odd shapes take the scalar kernels and UAPS_LOSS_EXACT
+// the torch-order ones.  UAPS_LOSS_IMPL=<0..2> overrides the choice (tuning knob, not part of the ABI).
+int pick_impl(int avail_vec, int flags, bool pass2) {
+    static const int forced = [] { const char* e = getenv("UAPS_LOSS_IMPL"); return e ? atoi(e) : -1; }();
+    if (flags & UAPS_LOSS_EXACT) return IMPL_EXACT;
+    if (avail_vec < 2) return IMPL_SCALAR;
+    if (forced >= 0 && forced <= IMPL_SCALAR) return forced;
+    if (avail_vec < 4) return IMPL_VEC2_PF;
+    return pass2 ? IMPL_VEC2_PF : IMPL_VEC4_PF;
+}
+
+int dispatch_k(int K, int C, int impl, bool sup, bool pass2, const LossArgs& a, float* partials, const float* sc,
+               const float* go, int* nblocks, cudaStream_t st) {
+    switch (K) {
+        case 1: return launch_loss_k<1>(C, impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 2: return launch_loss_k<2>(C, impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 3: return launch_loss_k<3>(C, impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 4: return launch_loss_k<4>(C, impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 5: return launch_loss_k<5>(C, impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 6: return launch_loss_k<6>(C, impl, sup, pass2, a, partials, sc, go, nblocks, st);
+    }
+    return UAPS_ERANGE;
 }
 
 }  // namespace
@@ -66,7 +84,7 @@ UAPS_API int uaps_loss_scalars_count(int K, int C) {
 }
 UAPS_API size_t uaps_loss_workspace_bytes(int K, int C) {
     if (K < 1 || K > KMAX || C < 2 || C > CMAX) return 0;
-    return WS_HEADER_BYTES + (size_t)LOSS_MAX_BLOCKS * sums_count(K, C) * sizeof(float);
+    return WS_HEADER_BYTES + (size_t)LOSS_MAX_BLOCKS * sums_count(K, C) * sizeof(float);   // partials[S][MAX_BLOCKS]
 }
 
 UAPS_API int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t HW,
@@ -87,23 +105,16 @@ UAPS_API int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t
             a.write_ev = 1;
         }
     }
-    const int vec = (flags & UAPS_LOSS_EXACT) ? 1 : final_vec(K, C, pick_vec(z, exp_var_out, K, HW));
-    a.labels = labels; a.pseudo = pseudo_out; a.HW = HW;
-    a.groups_per_image = (unsigned)(HW / vec);
-    a.ngroups = (unsigned)B * a.groups_per_image;
-    unsigned* ticket = reinterpret_cast<unsigned*>(workspace);
+    a.labels = labels; a.pseudo = pseudo_out; a.HW = HW; a.B = B;
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + WS_HEADER_BYTES);
-    const bool sup = labels != nullptr;
-    const bool exact = (flags & UAPS_LOSS_EXACT) != 0;
-    switch (K) {
-        case 1: return launch_pass1_k<1>(C, vec, sup, exact, a, ticket, partials, sums, stream);
-        case 2: return launch_pass1_k<2>(C, vec, sup, exact, a, ticket, partials, sums, stream);
-        case 3: return launch_pass1_k<3>(C, vec, sup, exact, a, ticket, partials, sums, stream);
-        case 4: return launch_pass1_k<4>(C, vec, sup, exact, a, ticket, partials, sums, stream);
-        case 5: return launch_pass1_k<5>(C, vec, sup, exact, a, ticket, partials, sums, stream);
-        case 6: return launch_pass1_k<6>(C, vec, sup, exact, a, ticket, partials, sums, stream);
-    }
-    return UAPS_ERANGE;
+    const int impl = pick_impl(pick_vec(z, exp_var_out, K, HW), flags, false);
+    int nblocks = 0;
+    rc = dispatch_k(K, C, impl, labels != nullptr, false, a, partials, nullptr, nullptr, &nblocks, stream);
+    if (rc != UAPS_OK) return rc;
+    const int S = sums_count(K, C);
+    loss_fold_kernel<<<ceil_div(S, 256 / kWarp), 256, 0, stream>>>(partials, S, (unsigned)nblocks, sums);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
 }
 
 UAPS_API int uaps_loss_finalize(const double* sums_global, int K, int C, int64_t N_global, float cw1,
@@ -130,19 +141,8 @@ UAPS_API int uaps_loss_pass2(const float* const* z, int K, int B, int C, int64_t
         a.w[k] = mix_w ? mix_w[k] : 0.f;
         a.out[k] = dz[k];
     }
-    const int vec = (flags & UAPS_LOSS_EXACT) ? 1 : final_vec(K, C, pick_vec(z, dz, K, HW));
-    a.labels = labels; a.pseudo = nullptr; a.HW = HW;
-    a.groups_per_image = (unsigned)(HW / vec);
-    a.ngroups = (unsigned)B * a.groups_per_image;
-    const bool sup = labels != nullptr;
-    const bool exact = (flags & UAPS_LOSS_EXACT) != 0;
-    switch (K) {
-        case 1: return launch_pass2_k<1>(C, vec, sup, exact, a, scalars, grad_out, stream);
-        case 2: return launch_pass2_k<2>(C, vec, sup, exact, a, scalars, grad_out, stream);
-        case 3: return launch_pass2_k<3>(C, vec, sup, exact, a, scalars, grad_out, stream);
-        case 4: return launch_pass2_k<4>(C, vec, sup, exact, a, scalars, grad_out, stream);
-        case 5: return launch_pass2_k<5>(C, vec, sup, exact, a, scalars, grad_out, stream);
-        case 6: return launch_pass2_k<6>(C, vec, sup, exact, a, scalars, grad_out, stream);
-    }
-    return UAPS_ERANGE;
+    a.labels = labels; a.pseudo = nullptr; a.HW = HW; a.B = B;
+    const int impl = pick_impl(pick_vec(z, dz, K, HW), flags, true);
+    int nblocks = 0;
+    return dispatch_k(K, C, impl, labels != nullptr, true, a, nullptr, scalars, grad_out, &nblocks, stream);
 }

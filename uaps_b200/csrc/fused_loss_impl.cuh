@@ -19,11 +19,17 @@ namespace loss {
 
 constexpr int KMAX = UAPS_KMAX;
 constexpr int CMAX = UAPS_CMAX;
-constexpr int LOSS_THREADS = 256;
-constexpr int LOSS_MAX_BLOCKS = 2048;
+constexpr int LOSS_THREADS = 128;
+constexpr int LOSS_MAX_BLOCKS = 640;            // >= 148 SMs x 4 CTAs; bounds the unrolled final fold
 constexpr int WS_HEADER_BYTES = 256;          // ticket counter lives in the first 4 bytes
 
 __host__ __device__ constexpr int sums_count(int K, int C) { return 3 * K + 2 * K * C + C; }
+// CTAs (of 128 threads) per SM the register allocator is asked to fit: estimated live registers =
+// the K*C*VEC logits + (pass 1) the running sums + ~64 of per-pixel state
+__host__ __device__ constexpr int min_ctas(int K, int C, int VEC, bool pass1) {
+    const int need = K * C * VEC + (pass1 ? sums_count(K, C) : K * C) + 64;
+    return need <= 124 ? 4 : (need <= 176 ? 3 : 2);
+}
 __host__ __device__ constexpr int scalars_count(int K, int C) { return UAPS_SC_BASE + 4 * K + 2 * K * C; }
 
 struct LossArgs {
@@ -35,21 +41,29 @@ struct LossArgs {
     long long HW;
     unsigned groups_per_image;   // HW / VEC
     unsigned ngroups;            // B * groups_per_image
+    int B;
     int write_ev;
 };
 
 // ---- per-pixel forward -------------------------------------------------------------------
+// Logarithms are carried in a mode-dependent unit U: natural logs in EXACT mode (U = 1), log2 in the
+// default mode (U = ln 2), so the MUFU results are used as they come and ln 2 is folded into the few
+// consumers.
+template <bool EXACT> struct LogUnit { static constexpr float U = EXACT ? 1.0f : 0.6931471805599453f; };
+
 template <int K, int C>
 struct PixelState {
     float p[K][C];   // softmax
-    float l[K][C];   // log-softmax
+    float l[K][C];   // log-softmax / U
     float q[C];      // mean prediction
-    float lq[C];     // log q (as computed; -inf when q == 0)
+    float lq[C];     // log q / U  (-inf when q == 0)
     float V[K];      // KL(q || p_k) summed over classes
     float E[K];      // exp(-V)
     int y;           // pseudo-label / label
 };
 
+// EXACT: torch's op order and roundings (cunn_SpatialSoftMaxForward / LogSoftMax): max, x - max, expf,
+// sequential sum, IEEE divide; log-softmax = (x - max) - logf(sum).
 template <int C>
 __device__ __forceinline__ void softmax_exact(const float (&z)[C], float (&p)[C], float (&l)[C]) {
     float m = z[0];
@@ -70,41 +84,61 @@ __device__ __forceinline__ void softmax_exact(const float (&z)[C], float (&p)[C]
     }
 }
 
-// ---- fast arithmetic (default mode) ---------------------------------------------------------
-// One MUFU per transcendental instead of the ~10-20 instruction precise expansions; every value
-// stays within ~1e-6 relative of the fp32 reference.  The pseudo-label is still bit-exact: see
-// `pixel_forward` -- whenever the fast mix cannot separate the top two classes by more than
-// kTieMargin (>> the ~1.5e-6 worst-case distance between the fast and the torch-order value),
-// the argmax is re-decided with the exact torch-order chain.
+// ---- default arithmetic: one MUFU per transcendental ------------------------------------------
+// exp2/rcp/log2 approximations (<= 2 ulp) instead of the 10-20 instruction IEEE expansions.  Two
+// things keep the results at the reference's accuracy:
+//  * log p_kc is taken as lg2.approx(p_kc) itself, and log q_c as lg2.approx(q_c): the KL maps are
+//    differences of the two, so the approximation's mantissa-dependent bias cancels (measured on
+//    B200, tools/logbias.cu: mean-V error vs fp64 <= that of IEEE logf in every regime, while
+//    t - lg2.approx(sum) is 10x worse when the decoders agree);
+//  * the pseudo-label is still bit-exact: whenever the fast mix cannot separate the top two classes
+//    by more than kTieMargin (>> the ~1.5e-6 worst-case distance between the fast and the torch-order
+//    value) the argmax is re-decided from the logits with the exact torch-order chain.
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kTieMargin = 2e-5f;
+constexpr float kLg2Floor = -120.0f;     // below this exp2 underflows (ftz): take log2 p from t - log2(sum) instead
 
-// PLOG: take log(s) with the precise logf.  Pass 1 sets it: the batch means of V_k (differences of
-// logs, ~1e-3 when the decoders agree) must not inherit the mantissa-dependent bias of lg2.approx.
-template <int C, bool PLOG>
-__device__ __forceinline__ void softmax_fast(const float (&z)[C], float (&p)[C], float (&l)[C]) {
+template <int C>
+__device__ __forceinline__ float softmax_fast(const float (&z)[C], float (&p)[C], float (&l2)[C]) {
     float m = z[0];
 #pragma unroll
     for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
-    float t[C], e[C];
-    float s = 0.f;
+    const float nm = -m * kLog2e;          // a rounding error here scales every e_c alike and cancels in p
+    float e[C];
+    float s = 0.f, tmin = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        t[c] = (z[c] - m) * kLog2e;           // subtract first: no cancellation error for large |z|
-        e[c] = ex2_approx(t[c]);
+        const float t = fmaf(z[c], kLog2e, nm);
+        tmin = fminf(tmin, t);
+        e[c] = ex2_approx(t);
         s += e[c];
     }
     const float r = rcp_approx(s);
-    const float nls = PLOG ? -logf(s) : -lg2_approx(s) * kLn2;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         p[c] = e[c] * r;
-        l[c] = fmaf(t[c], kLn2, nls);
+        l2[c] = lg2_approx(p[c]);
     }
+    return tmin;
+}
+
+// Rare fix-up (a class more than ~83 nats below its decoder's max): exp2 flushed p to 0, so take
+// log2 p from (z - max) * log2(e) - log2(sum) like the reference's log-softmax does.
+template <int C>
+__device__ __forceinline__ void log2_softmax_underflow_fix(const float (&z)[C], float (&l2)[C]) {
+    float m = z[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+    float t[C], s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { t[c] = (z[c] - m) * kLog2e; s += ex2_approx(t[c]); }
+    const float l2s = lg2_approx(s);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        if (t[c] < kLg2Floor) l2[c] = t[c] - l2s;
 }
 
 // torch-order argmax of the Dirichlet mix (UAPS_train.py:251-255), every rounding reproduced
@@ -123,23 +157,38 @@ __device__ __forceinline__ int argmax_exact(const float (&p)[K][C], const float 
     return y;
 }
 
+// Near-tie slow path: re-reads the pixel's logits (L1/L2 hits) so the hot loop keeps nothing alive for it.
 template <int K, int C>
-__device__ __noinline__ int argmax_exact_from_logits(const float (&z)[K][C], const float (&w)[K]) {
-    float p[K][C], l[C];
+__device__ __noinline__ int argmax_exact_gmem(const LossArgs& a, size_t pix_off) {
+    float p[K][C], w[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) softmax_exact<C>(z[k], p[k], l);
+    for (int k = 0; k < K; ++k) {
+        float z[C], l[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = __ldg(a.z[k] + pix_off + (size_t)c * a.HW);
+        softmax_exact<C>(z, p[k], l);
+        w[k] = a.w[k];
+    }
     return argmax_exact<K, C>(p, w);
 }
 
-template <int K, int C, bool SUP, bool EXACT, bool PLOG>
+template <int K, int C, bool SUP, bool EXACT>
 __device__ __forceinline__ void pixel_forward(const float (&z)[K][C], const float (&w)[K], int label,
-                                              PixelState<K, C>& st) {
+                                              const LossArgs& a, size_t pix_off, PixelState<K, C>& st) {
+    constexpr float U = LogUnit<EXACT>::U;
+    float tmin = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if constexpr (EXACT) softmax_exact<C>(z[k], st.p[k], st.l[k]);
-        else softmax_fast<C, PLOG>(z[k], st.p[k], st.l[k]);
+        else tmin = fminf(tmin, softmax_fast<C>(z[k], st.p[k], st.l[k]));
     }
     if constexpr (SUP) {
+        if constexpr (!EXACT) {
+            if (__builtin_expect(tmin < kLg2Floor, 0)) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) log2_softmax_underflow_fix<C>(z[k], st.l[k]);
+            }
+        }
         st.y = label;
 #pragma unroll
         for (int k = 0; k < K; ++k) { st.V[k] = 0.f; st.E[k] = 1.f; }
@@ -159,7 +208,14 @@ __device__ __forceinline__ void pixel_forward(const float (&z)[K][C], const floa
                 else if (mix > best) { second = best; best = mix; y = c; }
                 else second = fmaxf(second, mix);
             }
-            if (__builtin_expect(!(best - second > kTieMargin), 0)) y = argmax_exact_from_logits<K, C>(z, w);
+            // one rarely-taken branch per pixel covers both slow paths
+            if (__builtin_expect(!(best - second > kTieMargin) || tmin < kLg2Floor, 0)) {
+                if (!(best - second > kTieMargin)) y = argmax_exact_gmem<K, C>(a, pix_off);
+                if (tmin < kLg2Floor) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) log2_softmax_underflow_fix<C>(z[k], st.l[k]);
+                }
+            }
             st.y = y;
         }
         // mean prediction (:223) and KL maps (:226-236): V_k = sum_c xlogy(q,q) - q * l_kc
@@ -171,7 +227,7 @@ __device__ __forceinline__ void pixel_forward(const float (&z)[K][C], const floa
             for (int k = 1; k < K; ++k) acc = __fadd_rn(acc, st.p[k][c]);
             const float q = acc * (1.0f / K);
             st.q[c] = q;
-            st.lq[c] = (EXACT || PLOG) ? logf(q) : lg2_approx(q) * kLn2;
+            st.lq[c] = EXACT ? logf(q) : lg2_approx(q);
             h += (q == 0.f) ? 0.f : q * st.lq[c];
         }
 #pragma unroll
@@ -179,7 +235,7 @@ __device__ __forceinline__ void pixel_forward(const float (&z)[K][C], const floa
             float d = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) d = fmaf(st.q[c], st.l[k][c], d);
-            st.V[k] = h - d;
+            st.V[k] = (h - d) * U;
             st.E[k] = EXACT ? expf(-st.V[k]) : ex2_approx(-kLog2e * st.V[k]);
         }
     }
@@ -206,41 +262,88 @@ struct AccIdx {
     static constexpr int S = 3 * K + 2 * K * C + C;
 };
 
-template <int K, int C, int VEC, bool SUP, bool EXACT>
-__global__ void __launch_bounds__(LOSS_THREADS, 1)
-loss_pass1_kernel(const LossArgs a, unsigned* __restrict__ ticket, float* __restrict__ partials,
-                  double* __restrict__ sums) {
+// fold one pixel into the running sums.  The label's one-hot is applied as arithmetic masks (keeps
+// p/l in registers: a select chain would be turned into a local-memory indexed load)
+template <int K, int C, bool EXACT>
+__device__ __forceinline__ void accumulate_pixel(const PixelState<K, C>& st, float (&acc)[AccIdx<K, C>::S]) {
+    using AI = AccIdx<K, C>;
+    constexpr float U = LogUnit<EXACT>::U;
+    float oh[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        oh[c] = (st.y == c) ? 1.f : 0.f;
+        acc[AI::T + c] += oh[c];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        acc[AI::E + k] += st.E[k];
+        acc[AI::V + k] += st.V[k];
+        float ly = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            ly = fmaf(oh[c], st.l[k][c], ly);
+            acc[AI::I + k * C + c] = fmaf(oh[c], st.p[k][c], acc[AI::I + k * C + c]);
+            acc[AI::P + k * C + c] += st.p[k][c];
+        }
+        acc[AI::CE + k] = fmaf(-U, ly, acc[AI::CE + k]);
+    }
+}
+
+// block-level reduction of the running sums into this block's column of partials[S][LOSS_MAX_BLOCKS]
+template <int S, int THREADS>
+__device__ __forceinline__ void block_store_partials(float (&acc)[S], float* __restrict__ partials,
+                                                     float (*s_red)[S]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        const float r = warp_sum(acc[i]);
+        if (lane == 0) s_red[warp][i] = r;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += THREADS) {
+        float r = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < THREADS / kWarp; ++wv) r += s_red[wv][i];
+        partials[(size_t)i * LOSS_MAX_BLOCKS + blockIdx.x] = r;
+    }
+}
+
+template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF>
+__global__ void __launch_bounds__(LOSS_THREADS, min_ctas(K, C, PF ? 2 * VEC : VEC, true))
+loss_pass1_kernel(const __grid_constant__ LossArgs a, float* __restrict__ partials) {
     constexpr int S = sums_count(K, C);
     __shared__ float s_red[LOSS_THREADS / kWarp][S];
-    __shared__ bool s_last;
 
     float w[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) w[k] = a.w[k];
 
-    using AI = AccIdx<K, C>;
     float acc[S];
 #pragma unroll
     for (int i = 0; i < S; ++i) acc[i] = 0.f;
 
-    // register double buffering: the next group's K*C loads are in flight while this one is computed
-    // (the kernel runs at one CTA per SM, so latency is hidden by prefetch depth, not occupancy)
+    // software pipelining (PF): the next group's K*C loads are issued before this group is computed, so
+    // HBM latency overlaps the ~330 instructions/pixel instead of stalling the first consumer
     const unsigned stride = gridDim.x * LOSS_THREADS;
     unsigned g = blockIdx.x * LOSS_THREADS + threadIdx.x;
-    float zn[K][C][VEC];
-    if (g < a.ngroups) load_group<K, C, VEC>(a, g, zn);
+    float zn[PF ? K : 1][PF ? C : 1][PF ? VEC : 1];
+    if constexpr (PF) { if (g < a.ngroups) load_group<K, C, VEC>(a, g, zn); }
     for (; g < a.ngroups; g += stride) {
         const unsigned b = g / a.groups_per_image;
         const unsigned hw = (g - b * a.groups_per_image) * VEC;
         const size_t base = (size_t)b * C * a.HW + hw;
         float zv[K][C][VEC];
+        if constexpr (PF) {
 #pragma unroll
-        for (int k = 0; k < K; ++k)
+            for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int c = 0; c < C; ++c)
+                for (int c = 0; c < C; ++c)
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) zv[k][c][j] = zn[k][c][j];
-        if (g + stride < a.ngroups) load_group<K, C, VEC>(a, g + stride, zn);
+                    for (int j = 0; j < VEC; ++j) zv[k][c][j] = zn[k][c][j];
+            if (g + stride < a.ngroups) load_group<K, C, VEC>(a, g + stride, zn);
+        } else {
+            load_group<K, C, VEC>(a, g, zv);
+        }
         long long lab[VEC];
         if constexpr (SUP) {
 #pragma unroll
@@ -256,30 +359,11 @@ loss_pass1_kernel(const LossArgs a, unsigned* __restrict__ ticket, float* __rest
 #pragma unroll
                 for (int c = 0; c < C; ++c) z[k][c] = zv[k][c][j];
             PixelState<K, C> st;
-            pixel_forward<K, C, SUP, EXACT, true>(z, w, SUP ? (int)lab[j] : 0, st);
+            pixel_forward<K, C, SUP, EXACT>(z, w, SUP ? (int)lab[j] : 0, a, base + j, st);
             yv[j] = st.y;
-            // one-hot of the label as arithmetic masks (keeps p/l in registers: no select chains
-            // that the compiler would turn into a local-memory indexed load)
-            float oh[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                oh[c] = (st.y == c) ? 1.f : 0.f;
-                acc[AI::T + c] += oh[c];
-            }
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                ev[k][j] = st.E[k];
-                acc[AI::E + k] += st.E[k];
-                acc[AI::V + k] += st.V[k];
-                float ly = 0.f;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    ly = fmaf(oh[c], st.l[k][c], ly);
-                    acc[AI::I + k * C + c] = fmaf(oh[c], st.p[k][c], acc[AI::I + k * C + c]);
-                    acc[AI::P + k * C + c] += st.p[k][c];
-                }
-                acc[AI::CE + k] -= ly;
-            }
+            for (int k = 0; k < K; ++k) ev[k][j] = st.E[k];
+            accumulate_pixel<K, C, EXACT>(st, acc);
         }
         if (a.pseudo != nullptr) {
 #pragma unroll
@@ -292,42 +376,32 @@ loss_pass1_kernel(const LossArgs a, unsigned* __restrict__ ticket, float* __rest
         }
     }
 
-    // warp shuffle -> shared -> per-block partial
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < S; ++i) {
-        const float r = warp_sum(acc[i]);
-        if (lane == 0) s_red[warp][i] = r;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < S; i += LOSS_THREADS) {
-        float r = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < LOSS_THREADS / kWarp; ++wv) r += s_red[wv][i];
-        partials[(size_t)blockIdx.x * S + i] = r;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // last block: fold all per-block partials in fp64, fixed order -> deterministic
-    for (int i = warp; i < S; i += LOSS_THREADS / kWarp) {
-        double r = 0.0;
-        for (unsigned blk = lane; blk < gridDim.x; blk += kWarp)
-            r += (double)__ldcg(partials + (size_t)blk * S + i);
-        r = warp_sum(r);
-        if (lane == 0) sums[i] = r;
-    }
-    if (threadIdx.x == 0) *ticket = 0u;      // ready for the next call
+    block_store_partials<S, LOSS_THREADS>(acc, partials, s_red);
 }
 
 // ---- finalize (compiled only into the entry-point unit) -----------------------------------------
 #ifdef UAPS_LOSS_ENTRY
+// Deterministic fp64 fold of the per-block partials [S][LOSS_MAX_BLOCKS]: one warp per sum, every
+// lane's loads issued together (unrolled, predicated) so a row costs one L2 round trip.
+__global__ void __launch_bounds__(256) loss_fold_kernel(const float* __restrict__ partials, int S, unsigned nblocks,
+                                                        double* __restrict__ sums) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (256 / kWarp) + (threadIdx.x >> 5);
+    if (i >= S) return;
+    const float* row = partials + (size_t)i * LOSS_MAX_BLOCKS;
+    float v[LOSS_MAX_BLOCKS / kWarp];
+#pragma unroll
+    for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) {
+        const unsigned blk = u * kWarp + lane;
+        v[u] = (blk < nblocks) ? __ldcg(row + blk) : 0.f;
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) r += (double)v[u];
+    r = warp_sum(r);
+    if (lane == 0) sums[i] = r;
+}
+
 __global__ void loss_finalize_kernel(const double* __restrict__ sums, int K, int C, double N,
                                      float cw1, float cw2, int supervised, float* __restrict__ sc) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -386,59 +460,107 @@ struct GradConsts {
     float lam1, lam2, invNK;
 };
 
-template <int K, int C, int VEC, bool SUP, bool EXACT>
-__global__ void __launch_bounds__(LOSS_THREADS, 1)
-loss_pass2_kernel(const LossArgs a, const float* __restrict__ sc, const float* __restrict__ grad_out) {
-    __shared__ GradConsts<K, C> gc;
-    if (threadIdx.x == 0) {
-        // upstream gradient vector, laid out like scalars[] (only the five differentiable slots are read)
-        const float g_loss = grad_out[UAPS_SC_LOSS_U], g_ps = grad_out[UAPS_SC_PS_LOSS], g_unc = grad_out[UAPS_SC_L_UNCERT];
-        const float g_ce = grad_out[UAPS_SC_MEAN_CE], g_dice = grad_out[UAPS_SC_MEAN_DICE];
-        const float lam1 = g_loss * sc[UAPS_SC_CW1] + g_ps;
-        const float lam2 = g_loss * sc[UAPS_SC_CW2] + g_unc;
-        const float invN = sc[UAPS_SC_INV_N];
-        const float* ps = sc + UAPS_SC_BASE;
-        const float* Eb = ps + K;
-        const float* Ikc = ps + 4 * K;
-        const float* Card = Ikc + K * C;
-        gc.lam1 = lam1; gc.lam2 = lam2; gc.invNK = invN / K;
-        for (int k = 0; k < K; ++k) {
-            gc.psk[k] = ps[k];
-            const float half = lam1 * Eb[k] / (2.f * K);           // d loss / d ps_k * 0.5
-            const float dce = half + g_ce / K;                     // d loss / d CE_k
-            const float ddice = half + g_dice / K;                 // d loss / d Dice_k
-            gc.cce[k] = dce * invN;
-            for (int c = 0; c < C; ++c) {
-                const float den = Card[k * C + c] + 1e-7f;
-                gc.A[k][c] = -ddice * (2.f / C) / den;
-                gc.Bc[k][c] = ddice * (2.f / C) * Ikc[k * C + c] / (den * den);
-            }
+// one thread turns the loss scalars and the upstream gradient vector into the per-(k,c) constants
+template <int K, int C>
+__device__ __forceinline__ void load_grad_consts(GradConsts<K, C>& gc, const float* __restrict__ sc,
+                                                 const float* __restrict__ grad_out) {
+    // upstream gradient vector, laid out like scalars[] (only the five differentiable slots are read)
+    const float g_loss = grad_out[UAPS_SC_LOSS_U], g_ps = grad_out[UAPS_SC_PS_LOSS], g_unc = grad_out[UAPS_SC_L_UNCERT];
+    const float g_ce = grad_out[UAPS_SC_MEAN_CE], g_dice = grad_out[UAPS_SC_MEAN_DICE];
+    const float lam1 = g_loss * sc[UAPS_SC_CW1] + g_ps;
+    const float lam2 = g_loss * sc[UAPS_SC_CW2] + g_unc;
+    const float invN = sc[UAPS_SC_INV_N];
+    const float* ps = sc + UAPS_SC_BASE;
+    const float* Eb = ps + K;
+    const float* Ikc = ps + 4 * K;
+    const float* Card = Ikc + K * C;
+    gc.lam1 = lam1; gc.lam2 = lam2; gc.invNK = invN / K;
+    for (int k = 0; k < K; ++k) {
+        gc.psk[k] = ps[k];
+        const float half = lam1 * Eb[k] / (2.f * K);           // d loss / d ps_k * 0.5
+        const float dce = half + g_ce / K;                     // d loss / d CE_k
+        const float ddice = half + g_dice / K;                 // d loss / d Dice_k
+        gc.cce[k] = dce * invN;
+        for (int c = 0; c < C; ++c) {
+            const float den = Card[k * C + c] + 1e-7f;
+            gc.A[k][c] = -ddice * (2.f / C) / den;
+            gc.Bc[k][c] = ddice * (2.f / C) * Ikc[k * C + c] / (den * den);
         }
     }
+}
+
+// d loss / d z for one pixel (closed form checked against autograd in oracle/)
+template <int K, int C, bool SUP, bool EXACT>
+__device__ __forceinline__ void pixel_backward(const PixelState<K, C>& st, const GradConsts<K, C>& gc,
+                                               float (&dz)[K][C]) {
+    float gk[K];
+    float Gq[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) Gq[c] = 0.f;
+    if constexpr (!SUP) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            gk[k] = (gc.lam2 - gc.lam1 * gc.psk[k] * st.E[k]) * gc.invNK;
+#pragma unroll
+            for (int c = 0; c < C; ++c) Gq[c] += gk[k] * fmaf(LogUnit<EXACT>::U, st.lq[c] - st.l[k][c], 1.f);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) Gq[c] *= (1.0f / K);
+    }
+    float oh[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) oh[c] = (st.y == c) ? 1.f : 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float Gl[C], Gp[C];
+        float sGl = 0.f, dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float gl = -gc.cce[k] * oh[c];
+            if constexpr (!SUP) gl = fmaf(-gk[k], st.q[c], gl);
+            const float gp = fmaf(gc.A[k][c], oh[c], Gq[c] + gc.Bc[k][c]);
+            Gl[c] = gl; Gp[c] = gp;
+            sGl += gl;
+            dot = fmaf(st.p[k][c], gp, dot);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) dz[k][c] = fmaf(st.p[k][c], (Gp[c] - dot) - sGl, Gl[c]);
+    }
+}
+
+template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF>
+__global__ void __launch_bounds__(LOSS_THREADS, min_ctas(K, C, PF ? 2 * VEC : VEC, false))
+loss_pass2_kernel(const __grid_constant__ LossArgs a, const float* __restrict__ sc, const float* __restrict__ grad_out) {
+    __shared__ GradConsts<K, C> gc;
+    if (threadIdx.x == 0) load_grad_consts<K, C>(gc, sc, grad_out);
     __syncthreads();
 
     float w[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) w[k] = a.w[k];
 
-    // register double buffering: the next group's K*C loads are in flight while this one is computed
-    // (the kernel runs at one CTA per SM, so latency is hidden by prefetch depth, not occupancy)
+    // software pipelining (PF): the next group's K*C loads are issued before this group is computed, so
+    // HBM latency overlaps the ~330 instructions/pixel instead of stalling the first consumer
     const unsigned stride = gridDim.x * LOSS_THREADS;
     unsigned g = blockIdx.x * LOSS_THREADS + threadIdx.x;
-    float zn[K][C][VEC];
-    if (g < a.ngroups) load_group<K, C, VEC>(a, g, zn);
+    float zn[PF ? K : 1][PF ? C : 1][PF ? VEC : 1];
+    if constexpr (PF) { if (g < a.ngroups) load_group<K, C, VEC>(a, g, zn); }
     for (; g < a.ngroups; g += stride) {
         const unsigned b = g / a.groups_per_image;
         const unsigned hw = (g - b * a.groups_per_image) * VEC;
         const size_t base = (size_t)b * C * a.HW + hw;
         float zv[K][C][VEC];
+        if constexpr (PF) {
 #pragma unroll
-        for (int k = 0; k < K; ++k)
+            for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int c = 0; c < C; ++c)
+                for (int c = 0; c < C; ++c)
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) zv[k][c][j] = zn[k][c][j];
-        if (g + stride < a.ngroups) load_group<K, C, VEC>(a, g + stride, zn);
+                    for (int j = 0; j < VEC; ++j) zv[k][c][j] = zn[k][c][j];
+            if (g + stride < a.ngroups) load_group<K, C, VEC>(a, g + stride, zn);
+        } else {
+            load_group<K, C, VEC>(a, g, zv);
+        }
         long long lab[VEC];
         if constexpr (SUP) {
 #pragma unroll
@@ -452,42 +574,13 @@ loss_pass2_kernel(const LossArgs a, const float* __restrict__ sc, const float* _
 #pragma unroll
                 for (int c = 0; c < C; ++c) z[k][c] = zv[k][c][j];
             PixelState<K, C> st;
-            pixel_forward<K, C, SUP, EXACT, false>(z, w, SUP ? (int)lab[j] : 0, st);
-
-            float gk[K];
-            float Gq[C];
+            pixel_forward<K, C, SUP, EXACT>(z, w, SUP ? (int)lab[j] : 0, a, base + j, st);
+            float dz[K][C];
+            pixel_backward<K, C, SUP, EXACT>(st, gc, dz);
 #pragma unroll
-            for (int c = 0; c < C; ++c) Gq[c] = 0.f;
-            if constexpr (!SUP) {
+            for (int k = 0; k < K; ++k)
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    gk[k] = (gc.lam2 - gc.lam1 * gc.psk[k] * st.E[k]) * gc.invNK;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) Gq[c] += gk[k] * (st.lq[c] + 1.f - st.l[k][c]);
-                }
-#pragma unroll
-                for (int c = 0; c < C; ++c) Gq[c] *= (1.0f / K);
-            }
-            float oh[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) oh[c] = (st.y == c) ? 1.f : 0.f;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                float Gl[C], Gp[C];
-                float sGl = 0.f, dot = 0.f;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    float gl = -gc.cce[k] * oh[c];
-                    if constexpr (!SUP) gl = fmaf(-gk[k], st.q[c], gl);
-                    const float gp = fmaf(gc.A[k][c], oh[c], Gq[c] + gc.Bc[k][c]);
-                    Gl[c] = gl; Gp[c] = gp;
-                    sGl += gl;
-                    dot = fmaf(st.p[k][c], gp, dot);
-                }
-#pragma unroll
-                for (int c = 0; c < C; ++c)
-                    zv[k][c][j] = fmaf(st.p[k][c], (Gp[c] - dot) - sGl, Gl[c]);
-            }
+                for (int c = 0; c < C; ++c) zv[k][c][j] = dz[k][c];
         }
 #pragma unroll
         for (int k = 0; k < K; ++k)
@@ -496,10 +589,15 @@ loss_pass2_kernel(const LossArgs a, const float* __restrict__ sc, const float* _
     }
 }
 
-
 // ---- per-K launchers (one translation unit per K keeps nvcc parallel and compile time bounded) ---
-// widest per-thread pixel vector that keeps the K*C*VEC logits in registers without spilling
-__host__ __device__ constexpr int max_vec(int K, int C) { return K * C <= 24 ? 4 : (K * C <= 48 ? 2 : 1); }
+// Kernel variants.  Measured on B200 (profiles/r01_loss_variants.txt): software-pipelined register
+// kernels beat both the plain ones (first-use stall on the K*C loads was 36% of all warp stall
+// samples) and a cp.async.bulk/mbarrier shared-memory ring (which removed that stall but lost the
+// cross-pixel ILP the per-thread vector gives); pass 1 likes 4 pixels/thread, pass 2 two.
+enum LossImpl { IMPL_VEC4_PF = 0, IMPL_VEC2_PF = 1, IMPL_SCALAR = 2, IMPL_EXACT = 3 };
+
+__host__ __device__ constexpr bool has_vec4(int K, int C) { return K * C <= 16; }
+__host__ __device__ constexpr bool has_vec2(int K, int C) { return K * C <= 24; }
 
 template <typename Kern>
 inline int grid_for(Kern kern, unsigned ngroups) {
@@ -511,55 +609,55 @@ inline int grid_for(Kern kern, unsigned ngroups) {
     return (int)(want < cap ? want : cap);
 }
 
-template <int K, int C, int VEC, bool SUP, bool EXACT>
-inline int launch_pass1(const LossArgs& a, unsigned* ticket, float* partials, double* sums, cudaStream_t st) {
-    auto kern = loss_pass1_kernel<K, C, VEC, SUP, EXACT>;
-    kern<<<grid_for(kern, a.ngroups), LOSS_THREADS, 0, st>>>(a, ticket, partials, sums);
-    UAPS_LAUNCH_CHECK();
-    return UAPS_OK;
-}
-template <int K, int C, int VEC, bool SUP, bool EXACT>
-inline int launch_pass2(const LossArgs& a, const float* sc, const float* go, cudaStream_t st) {
-    auto kern = loss_pass2_kernel<K, C, VEC, SUP, EXACT>;
-    kern<<<grid_for(kern, a.ngroups), LOSS_THREADS, 0, st>>>(a, sc, go);
+template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF>
+inline int launch_reg(bool pass2, LossArgs a, float* partials, const float* sc, const float* go, int* nblocks,
+                      cudaStream_t st) {
+    a.groups_per_image = (unsigned)(a.HW / VEC);
+    a.ngroups = (unsigned)a.B * a.groups_per_image;
+    if (!pass2) {
+        auto kern = loss_pass1_kernel<K, C, VEC, SUP, EXACT, PF>;
+        static const int grid_cap = grid_for(kern, 0x7fffffffu);       // occupancy query once per instantiation
+        const long long want = ceil_div<long long>(a.ngroups, LOSS_THREADS);
+        *nblocks = (int)(want < grid_cap ? want : grid_cap);
+        kern<<<*nblocks, LOSS_THREADS, 0, st>>>(a, partials);
+    } else {
+        auto kern = loss_pass2_kernel<K, C, VEC, SUP, EXACT, PF>;
+        static const int grid_cap = grid_for(kern, 0x7fffffffu);
+        const long long want = ceil_div<long long>(a.ngroups, LOSS_THREADS);
+        *nblocks = (int)(want < grid_cap ? want : grid_cap);
+        kern<<<*nblocks, LOSS_THREADS, 0, st>>>(a, sc, go);
+    }
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
 
-// variants per (K, C): fast math at the widest vector, fast math scalar (odd HW / unaligned), and
-// the exact torch-order arithmetic (validation mode, scalar only)
-#define UAPS_LOSS_CASE(CC)                                                                          \
-    case CC: {                                                                                      \
-        constexpr int VM = max_vec(K, CC);                                                          \
-        if (exact) return sup ? CALL(K, CC, 1, true, true) : CALL(K, CC, 1, false, true);           \
-        if (vec == VM && VM > 1)                                                                    \
-            return sup ? CALL(K, CC, VM, true, false) : CALL(K, CC, VM, false, false);              \
-        return sup ? CALL(K, CC, 1, true, false) : CALL(K, CC, 1, false, false);                    \
-    }
+template <int K, int C>
+inline int launch_kc(int impl, bool sup, bool pass2, const LossArgs& a, float* partials, const float* sc,
+                     const float* go, int* nblocks, cudaStream_t st) {
+#define UAPS_RUN(VEC, EXACT, PF)                                                                       \
+    (sup ? launch_reg<K, C, VEC, true, EXACT, PF>(pass2, a, partials, sc, go, nblocks, st)             \
+         : launch_reg<K, C, VEC, false, EXACT, PF>(pass2, a, partials, sc, go, nblocks, st))
+    if (impl == IMPL_EXACT) return UAPS_RUN(1, true, false);
+    if constexpr (has_vec4(K, C)) { if (impl == IMPL_VEC4_PF) return UAPS_RUN(4, false, true); }
+    if constexpr (has_vec2(K, C)) { if (impl == IMPL_VEC4_PF || impl == IMPL_VEC2_PF) return UAPS_RUN(2, false, true); }
+    return UAPS_RUN(1, false, false);
+#undef UAPS_RUN
+}
 
 template <int K>
-int launch_pass1_k(int C, int vec, bool sup, bool exact, const LossArgs& a, unsigned* ticket, float* partials,
-                   double* sums, cudaStream_t st) {
-#define CALL(KK, CC, VV, SS, EE) launch_pass1<KK, CC, VV, SS, EE>(a, ticket, partials, sums, st)
+int launch_loss_k(int C, int impl, bool sup, bool pass2, const LossArgs& a, float* partials, const float* sc,
+                  const float* go, int* nblocks, cudaStream_t st) {
     switch (C) {
-        UAPS_LOSS_CASE(2) UAPS_LOSS_CASE(3) UAPS_LOSS_CASE(4) UAPS_LOSS_CASE(5)
-        UAPS_LOSS_CASE(6) UAPS_LOSS_CASE(7) UAPS_LOSS_CASE(8)
+        case 2: return launch_kc<K, 2>(impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 3: return launch_kc<K, 3>(impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 4: return launch_kc<K, 4>(impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 5: return launch_kc<K, 5>(impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 6: return launch_kc<K, 6>(impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 7: return launch_kc<K, 7>(impl, sup, pass2, a, partials, sc, go, nblocks, st);
+        case 8: return launch_kc<K, 8>(impl, sup, pass2, a, partials, sc, go, nblocks, st);
     }
-#undef CALL
     return UAPS_ERANGE;
 }
-template <int K>
-int launch_pass2_k(int C, int vec, bool sup, bool exact, const LossArgs& a, const float* sc, const float* go,
-                   cudaStream_t st) {
-#define CALL(KK, CC, VV, SS, EE) launch_pass2<KK, CC, VV, SS, EE>(a, sc, go, st)
-    switch (C) {
-        UAPS_LOSS_CASE(2) UAPS_LOSS_CASE(3) UAPS_LOSS_CASE(4) UAPS_LOSS_CASE(5)
-        UAPS_LOSS_CASE(6) UAPS_LOSS_CASE(7) UAPS_LOSS_CASE(8)
-    }
-#undef CALL
-    return UAPS_ERANGE;
-}
-#undef UAPS_LOSS_CASE
 
 }  // namespace loss
 }  // namespace uaps

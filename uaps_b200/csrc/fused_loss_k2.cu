@@ -1,6 +1,5 @@
-// Instantiates the fused-loss kernels for K = 2 decoders (all C; fast/exact, vector/scalar, both modes).
+// Instantiates the fused-loss kernels for K = 2 decoders (all C; tiled / register, fast / exact, both modes).
 #include "fused_loss_impl.cuh"
 namespace uaps { namespace loss {
-template int launch_pass1_k<2>(int, int, bool, bool, const LossArgs&, unsigned*, float*, double*, cudaStream_t);
-template int launch_pass2_k<2>(int, int, bool, bool, const LossArgs&, const float*, const float*, cudaStream_t);
+template int launch_loss_k<2>(int, int, bool, bool, const LossArgs&, float*, const float*, const float*, int*, cudaStream_t);
 } }
