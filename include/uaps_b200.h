@@ -156,6 +156,26 @@ int uaps_perturb3_bwd(const float* g_noise, const float* g_drop, const float* g_
                       double p_drop, const float* attention, const uint32_t* smax_enc, float u,
                       float* dx, int B, int C, int64_t HW, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 / TMEM / TMA (3x3 pad 1 or 1x1, stride 1), bf16 operands, fp32
+ * accumulation.  Replaces the cuDNN calls behind nn.Conv2d in utilities/UAPS_unet.py:36,41 (ConvBlock),
+ * :73 (UpBlock conv1x1), :138 (out_conv) and, with transpose = 1 packing, their data gradients.
+ * Activations: NHWC bf16, channel pitch c*_stride (a multiple of 8 that covers the channel count
+ * rounded up to 16; padding channels must be zero).  x2 (nullable, cin2 = 0) is a second K segment:
+ * conv(cat([x1, x2], channel)) without materialising the concat (UAPS_unet.py:85).
+ * Output: bf16 NHWC with channel pitch out_c_stride, or fp32 NCHW (out_nchw_f32 = 1, the layout the
+ * fused loss kernel consumes).  bias: fp32 [cout] or NULL.
+ * ------------------------------------------------------------------------------------------- */
+size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks);
+/* w: device fp32 in torch layout [cout][cin1+cin2][ks][ks]; transpose = 1 packs the data-gradient
+ * kernel W'[ci][co][r][s] = W[co][ci][ks-1-r][ks-1-s] (then cout/cin name W's input/output channels
+ * swapped: pass cout = W's Cin, cin1 = W's Cout). */
+int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks,
+                           int transpose, cudaStream_t stream);
+int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
+                    const float* bias, void* out, int out_c_stride, int out_nchw_f32,
+                    int B, int H, int W, int cin1, int cin2, int cout, int ks, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

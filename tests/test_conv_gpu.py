@@ -1,0 +1,94 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution against torch's conv2d on the same bf16-rounded
+operands (fp32 accumulation both sides).  Tolerance 1e-2 of the output scale, as BASELINE.json's
+north_star states for bf16 conv activations; observed errors are ~1e-3 (bf16 output rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, b, ks):
+    xr, wr = x.bfloat16().float(), w.bfloat16().float()
+    return F.conv2d(xr, wr, b, padding=ks // 2)
+
+
+# (B, H, W, Cin, Cout, ks): every distinct layer shape of UNet_UAPS at 256x256 plus edge cases
+SHAPES = [
+    (2, 64, 64, 3, 16, 3),       # in_conv first conv (Cin padded 3 -> 16)
+    (2, 64, 64, 16, 16, 3),      # level-0 blocks
+    (2, 32, 32, 16, 32, 3),      # down1
+    (2, 32, 32, 32, 32, 3),
+    (2, 16, 16, 32, 64, 3),      # down2
+    (2, 16, 16, 64, 64, 3),
+    (1, 32, 32, 64, 128, 3),     # down3
+    (1, 32, 32, 128, 128, 3),
+    (1, 16, 16, 128, 256, 3),    # down4: two N tiles
+    (1, 16, 16, 256, 256, 3),
+    (1, 16, 16, 256, 128, 1),    # up1.conv1x1
+    (2, 32, 32, 32, 16, 1),      # up4.conv1x1
+    (2, 64, 64, 16, 4, 3),       # out_conv (N padded 4 -> 16)
+    (1, 48, 40, 16, 16, 3),      # partial tiles in y (48 = 3 x 16) and x (40 = 5 x 8)
+    (1, 15, 40, 128, 128, 3),    # KoSDD2 240x640 at level 4: H not a multiple of the tile
+    (1, 24, 20, 32, 32, 3),      # W not a multiple of 8
+]
+
+
+@pytest.mark.parametrize("B,H,W,ci,co,ks", SHAPES)
+def test_fprop_matches_torch(B, H, W, ci, co, ks):
+    from uaps_b200.conv import PackedConv, from_nhwc, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B * 1000 + H + ci * 7 + co)
+    x = torch.randn(B, ci, H, W, generator=g).to(dev)
+    w = (torch.randn(co, ci, ks, ks, generator=g) * (2.0 / (ci * ks * ks)) ** 0.5).to(dev)
+    b = torch.randn(co, generator=g).to(dev)
+    ref = _ref(x, w, b, ks)
+    conv = PackedConv(w, b)
+    y = conv(to_nhwc_bf16(x))
+    out = from_nhwc(y, co)
+    err = (out - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), (err, ref.abs().max().item())
+    if y.shape[-1] > co:
+        assert y[..., co:].abs().max().item() == 0.0          # padding channels stay zero
+
+
+def test_concat_two_segments():
+    """conv(cat([skip, up])) as two K segments (UpBlock, UAPS_unet.py:85-86) without the concat."""
+    from uaps_b200.conv import PackedConv, from_nhwc, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    for c in (16, 32, 64, 128):
+        skip, up = torch.randn(2, c, 32, 32, generator=g).to(dev), torch.randn(2, c, 32, 32, generator=g).to(dev)
+        w = (torch.randn(c, 2 * c, 3, 3, generator=g) * (1.0 / (18 * c)) ** 0.5).to(dev)
+        b = torch.randn(c, generator=g).to(dev)
+        ref = _ref(torch.cat([skip, up], 1), w, b, 3)
+        out = from_nhwc(PackedConv(w, b, cin_split=c)(to_nhwc_bf16(skip), to_nhwc_bf16(up)), c)
+        assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item(), c
+
+
+def test_logits_output_nchw_fp32():
+    """out_conv writes fp32 NCHW directly -- the layout the fused loss kernel reads."""
+    from uaps_b200.conv import PackedConv, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(6)
+    for C in (2, 4, 7):
+        x = torch.randn(2, 16, 64, 64, generator=g).to(dev)
+        w, b = (torch.randn(C, 16, 3, 3, generator=g) * 0.1).to(dev), torch.randn(C, generator=g).to(dev)
+        ref = _ref(x, w, b, 3)
+        out = PackedConv(w, b)(to_nhwc_bf16(x), out_nchw_f32=True)
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()    # fp32 output: only operand rounding
+
+
+def test_data_gradient_via_transposed_packing():
+    """dX of a 3x3 conv = conv of dY with the rotated, channel-transposed kernel (same tcgen05 kernel)."""
+    from uaps_b200.conv import PackedConv, from_nhwc, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(8)
+    for ci, co in ((16, 32), (64, 64), (128, 64)):
+        x = torch.randn(2, ci, 32, 32, generator=g).to(dev).requires_grad_(True)
+        w = (torch.randn(co, ci, 3, 3, generator=g) * 0.05).to(dev)
+        dy = torch.randn(2, co, 32, 32, generator=g).to(dev)
+        F.conv2d(x, w.bfloat16().float(), padding=1).backward(dy.bfloat16().float())
+        dx = from_nhwc(PackedConv(w, None, transpose=True)(to_nhwc_bf16(dy)), ci)
+        assert (dx - x.grad).abs().max().item() <= 1e-2 * x.grad.abs().max().item(), (ci, co)

@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(lambda s: _compile(s, verbose), stale))
     objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
     if stale or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-lcuda"]
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

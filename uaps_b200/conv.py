@@ -1,0 +1,77 @@
+"""tcgen05 implicit-GEMM convolution: Python face of uaps_conv_* (include/uaps_b200.h).
+
+Activations are NHWC bf16 ("channels-last") with the channel count padded to a multiple of 16;
+``to_nhwc_bf16`` / ``from_nhwc`` convert from and to the reference's NCHW fp32 tensors
+(utilities/UAPS_unet.py works in NCHW fp32 throughout).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] float -> [B,H,W,pad16(C)] bf16 with zero padding channels."""
+    B, C, H, W = x.shape
+    out = torch.zeros((B, H, W, pad16(C)), dtype=torch.bfloat16, device=x.device)
+    out[..., :C] = x.permute(0, 2, 3, 1)
+    return out
+
+
+def from_nhwc(y: torch.Tensor, c: int) -> torch.Tensor:
+    """[B,H,W,Cp] bf16 -> [B,c,H,W] fp32."""
+    return y[..., :c].permute(0, 3, 1, 2).float().contiguous()
+
+
+class PackedConv:
+    """Weights of one conv layer packed into the kernel's shared-memory stage image (bf16, pre-swizzled)."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], cin_split=None, transpose: bool = False):
+        L.require_cuda(weight)
+        w = weight.detach().float().contiguous()
+        co, ci, ks, ks2 = w.shape
+        assert ks == ks2 and ks in (1, 3)
+        if transpose:                       # data-gradient conv: output channels = W's input channels
+            assert cin_split is None
+            self.cout, self.cin1, self.cin2 = ci, co, 0
+        else:
+            self.cout = co
+            self.cin1, self.cin2 = (ci, 0) if cin_split is None else (cin_split, ci - cin_split)
+        self.ks = ks
+        nbytes = L.lib().uaps_conv_packed_bytes(self.cout, self.cin1, self.cin2, ks)
+        if nbytes == 0:
+            raise RuntimeError("unsupported convolution shape")
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        with torch.cuda.device(w.device):
+            L.check(L.lib().uaps_conv_pack_weights(w.data_ptr(), self.packed.data_ptr(), self.cout, self.cin1, self.cin2,
+                                                   ks, int(transpose), L.stream_ptr()), "uaps_conv_pack_weights")
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+
+    def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, out_nchw_f32: bool = False) -> torch.Tensor:
+        L.require_cuda(x1)
+        assert x1.dtype == torch.bfloat16 and x1.is_contiguous() and x1.dim() == 4
+        B, H, W, c1s = x1.shape
+        c2s = 0
+        if self.cin2 > 0:
+            assert x2 is not None and x2.dtype == torch.bfloat16 and x2.is_contiguous() and x2.shape[:3] == x1.shape[:3]
+            c2s = x2.shape[3]
+        if out_nchw_f32:
+            out = torch.empty((B, self.cout, H, W), dtype=torch.float32, device=x1.device)
+            ocs = 0
+        else:
+            ocs = pad16(self.cout)
+            alloc = torch.zeros if ocs != self.cout else torch.empty
+            out = alloc((B, H, W, ocs), dtype=torch.bfloat16, device=x1.device)
+        with torch.cuda.device(x1.device):
+            L.check(L.lib().uaps_conv_fprop(x1.data_ptr(), c1s, None if x2 is None else x2.data_ptr(), c2s,
+                                            self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(),
+                                            out.data_ptr(), ocs, int(out_nchw_f32), B, H, W, self.cin1, self.cin2,
+                                            self.cout, self.ks, L.stream_ptr()), "uaps_conv_fprop")
+        return out

@@ -1,0 +1,424 @@
+// Implicit-GEMM convolution (3x3 pad 1 / 1x1, stride 1) on the 5th-gen tensor cores:
+// tcgen05.mma with the accumulator in TMEM, activations fed by TMA, weights by bulk-async copies.
+// Replaces the cuDNN calls behind nn.Conv2d in ConvBlock / UpBlock / out_conv of
+// utilities/UAPS_unet.py:31-47, 65-86, 138-139 (forward), and -- with rotated/transposed packed
+// weights -- their data-gradient.
+//
+// GEMM view: M = 128 output pixels (a 16 x 8 spatial tile of one image), N = output channels of
+// this CTA (N_TILE <= 128), K = taps x input channels.  Activations are NHWC bf16.
+//
+//   A operand.  One TMA box {CK channels, 8 x, 16+2 y, 1 n} per horizontal tap s in {-1,0,+1} lands
+//   as a K-major [144 rows][CK] tile whose rows are (y, x) and whose row pitch (CK*2 B) equals the
+//   swizzle span.  Eight consecutive rows = one image row = exactly one swizzle atom, so the three
+//   vertical taps r are the SAME tile read at row offsets 0 / 8 / 16: atom-aligned descriptor starts,
+//   no re-load.  Out-of-image coordinates (incl. negative) are zero-filled by TMA = the conv padding.
+//   3 loads serve 9 taps (3.4x operand traffic out of L2 instead of 9x).
+//   A concatenated input (UpBlock's torch.cat([skip, up]), :85) is two K segments with two tensor
+//   maps: the concat is never materialised.
+//
+//   B operand.  Weights are packed once per step into the exact shared-memory image
+//   [n_tile][segment][chunk][s][r][N_TILE][CK] bf16 with the 16-byte swizzle already applied, so a
+//   stage's three r-blocks are one contiguous cp.async.bulk.
+//
+//   D.  128 lanes x N_TILE fp32 columns of TMEM.  Epilogue: tcgen05.ld 32x32b, + bias, -> bf16 NHWC
+//   (or fp32 NCHW for the logits that feed the fused loss kernel).
+//
+// One output tile per CTA, 4 warps: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer
+// (warp 1 owns the TMEM allocation), all four warps = epilogue.  Small layers hide latency by many
+// co-resident CTAs (their stages are a few KB), big layers by the STAGES-deep ring inside the CTA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace uaps {
+namespace conv {
+
+constexpr int TILE_H = 16, TILE_W = 8, TILE_M = TILE_H * TILE_W;   // 128 pixels = UMMA M
+constexpr int THREADS = 128;
+constexpr int MAX_STAGES = 4;
+
+struct ConvArgs {
+    int B, H, W;
+    int cout;            // real output channels (stores are masked beyond it)
+    int cout_stride;     // channel pitch of the NHWC output (>= cout)
+    int n_tile;          // output channels per CTA, multiple of 16
+    int nseg;            // 1 or 2 K segments
+    int chunks[2];       // CK-wide channel chunks per segment
+    int ks;              // 1 or 3
+    int stages;
+    int tiles_x, tiles_y;
+    int out_nchw_f32;    // 1: write fp32 NCHW (logits), 0: bf16 NHWC
+    const float* bias;   // [>= n_tiles * n_tile] or null
+    const unsigned char* w_packed;
+    void* out;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c, int x, int y, int n, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(x), "r"(y), "r"(n) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO = 8 rows |
+// version 1 | layout type.  Row pitch == swizzle span, so SBO = 8 * span.
+template <int CK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    constexpr uint64_t span = CK * 2;                                    // 32 / 64 / 128 bytes
+    constexpr uint64_t layout = (CK == 64) ? 2 : (CK == 32 ? 4 : 6);     // SWIZZLE_128B / 64B / 32B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (((8 * span) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, both K-major, N>>3, M>>4
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+template <int CK>
+__global__ void __launch_bounds__(THREADS)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                  const __grid_constant__ ConvArgs a) {
+    constexpr int ROW_BYTES = CK * 2;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], done_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int halo = a.ks - 1;
+    const int a_bytes = (TILE_H + halo) * TILE_W * ROW_BYTES;
+    const int b_bytes = a.ks * a.n_tile * ROW_BYTES;
+    const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
+    const int iters = (a.chunks[0] + (a.nseg > 1 ? a.chunks[1] : 0)) * a.ks;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % a.tiles_x; t /= a.tiles_x;
+    const int ty = t % a.tiles_y; t /= a.tiles_y;
+    const int n_img = t;
+    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+    const int n_tile_idx = blockIdx.y;
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < a.n_tile) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer --------------------------------------------------------------------
+            const unsigned char* wsrc = a.w_packed + (size_t)n_tile_idx * iters * b_bytes;
+            int it = 0;
+            for (int seg = 0; seg < a.nseg; ++seg) {
+                const CUtensorMap* map = seg == 0 ? &map0 : &map1;
+                for (int ch = 0; ch < a.chunks[seg]; ++ch) {
+                    for (int s = 0; s < a.ks; ++s, ++it) {
+                        const int st = it % a.stages;
+                        mbar_wait(empty_bar + st, ((it / a.stages) & 1) ^ 1);
+                        unsigned char* sa = smem + (size_t)st * stage_bytes;
+                        mbar_expect_tx(full_bar + st, a_bytes + b_bytes);
+                        tma_load_4d(sa, map, ch * CK, x0 + s - halo / 2, y0 - halo / 2, n_img, full_bar + st);
+                        bulk_g2s(sa + a_bytes, wsrc + (size_t)it * b_bytes, b_bytes, full_bar + st);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----------------------------------------------------------------------
+            const uint32_t idesc = make_idesc(a.n_tile);
+            for (int it = 0; it < iters; ++it) {
+                const int st = it % a.stages;
+                mbar_wait(full_bar + st, (it / a.stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+                for (int r = 0; r < a.ks; ++r) {
+#pragma unroll
+                    for (int kk = 0; kk < CK / 16; ++kk) {
+                        const uint64_t ad = make_desc<CK>(sa + r * (TILE_W * ROW_BYTES) + kk * 32);
+                        const uint64_t bd = make_desc<CK>(sb + r * (a.n_tile * ROW_BYTES) + kk * 32);
+                        umma_bf16(tmem_d, ad, bd, idesc, (it | r | kk) != 0);
+                    }
+                }
+                umma_commit(empty_bar + st);           // frees the stage when these MMAs have read it
+            }
+            umma_commit(&done_bar);                    // accumulator complete
+        }
+        __syncwarp();
+    }
+
+    // ---- epilogue: TMEM -> registers -> global ----------------------------------------------------
+    mbar_wait(&done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = warp * 32 + lane;
+    const int y = y0 + row / TILE_W, x = x0 + row % TILE_W;
+    const bool valid = (y < a.H) && (x < a.W);
+    const int n0 = n_tile_idx * a.n_tile;
+    for (int j = 0; j < a.n_tile / 16; ++j) {
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + j * 16, v);
+        const int c0 = n0 + j * 16;
+        if (a.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += (c0 + i < a.cout) ? __ldg(a.bias + c0 + i) : 0.f;
+        }
+        if (!valid) continue;
+        if (a.out_nchw_f32) {
+            float* o = reinterpret_cast<float*>(a.out);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < a.cout) o[(((size_t)n_img * a.cout + c0 + i) * a.H + y) * a.W + x] = v[i];
+        } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + (((size_t)n_img * a.H + y) * a.W + x) * a.cout_stride + c0;
+            if (c0 + 16 <= a.cout) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* o4 = reinterpret_cast<uint4*>(o);
+                o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < a.cout) o[i] = __float2bfloat16_rn(v[i]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// ---- weight packing: torch [Cout][Cin][ks][ks] fp32 -> pre-swizzled bf16 stage images -----------------
+// dst block (nt, it = ((seg, chunk), s), r) is [n_tile][CK] bf16; 16-byte chunk j of row n is stored at
+// chunk (j ^ swz(n)) -- Swizzle<3|2|1,4,3> on the byte address, the pattern TMA / UMMA use.
+struct PackArgs {
+    const float* w; unsigned char* dst;
+    int cout, cin_total, ks, n_tile, n_tiles, ck, nseg, seg_c[2], seg_pad[2];   // seg_pad: channels incl. zero padding
+    int transpose;       // 1: pack W'[ci][co][r][s] = W[co][ci][ks-1-r][ks-1-s] (data-gradient conv); cout/cin are those of W'
+};
+__global__ void pack_weights_kernel(PackArgs p) {
+    const int chunks_per_row = p.ck / 8;
+    const int chunks0 = p.seg_pad[0] / p.ck, chunks1 = p.nseg > 1 ? p.seg_pad[1] / p.ck : 0;
+    const int iters = (chunks0 + chunks1) * p.ks;
+    const long long total = (long long)p.n_tiles * iters * p.ks * p.n_tile * chunks_per_row;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long t = idx;
+        const int j = t % chunks_per_row; t /= chunks_per_row;
+        const int n = t % p.n_tile; t /= p.n_tile;
+        const int r = t % p.ks; t /= p.ks;
+        const int it = t % iters; t /= iters;
+        const int nt = (int)t;
+        const int s = it % p.ks;
+        int ch = it / p.ks, seg = 0;
+        if (ch >= chunks0) { ch -= chunks0; seg = 1; }
+        const int co = nt * p.n_tile + n;
+        const int span_rows = 128 / (p.ck * 2);                         // rows per 128 bytes: 1 / 2 / 4
+        const int swz = (n / span_rows) % chunks_per_row;               // bits [7,7+B) of the byte address
+        __nv_bfloat16 vals[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int cl = ch * p.ck + j * 8 + e;                       // channel inside the segment
+            float v = 0.f;
+            if (co < p.cout && cl < p.seg_c[seg]) {
+                const int ci = (seg == 0 ? 0 : p.seg_c[0]) + cl;
+                if (!p.transpose) v = p.w[(((size_t)co * p.cin_total + ci) * p.ks + r) * p.ks + s];
+                else v = p.w[(((size_t)ci * p.cout + co) * p.ks + (p.ks - 1 - r)) * p.ks + (p.ks - 1 - s)];
+            }
+            vals[e] = __float2bfloat16_rn(v);
+        }
+        const size_t block = (((size_t)nt * iters + it) * p.ks + r) * p.n_tile * (p.ck * 2);
+        const size_t off = block + (size_t)n * (p.ck * 2) + (size_t)((j ^ swz) * 16);
+        *reinterpret_cast<uint4*>(p.dst + off) = *reinterpret_cast<const uint4*>(vals);
+    }
+}
+
+inline int pick_ck(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+inline int pick_n_tile(int cout) {
+    const int padded = (cout + 15) / 16 * 16;
+    return padded <= 128 ? padded : 128;
+}
+
+}  // namespace conv
+}  // namespace uaps
+
+using namespace uaps;
+using namespace uaps::conv;
+
+namespace {
+struct Plan {
+    int ck, n_tile, n_tiles, seg_pad[2], chunks[2], nseg, iters;
+    size_t packed_bytes;
+};
+// cin2 == 0: single segment.  Channels are zero-padded up to a multiple of 16 inside a segment.
+int make_plan(int cout, int cin1, int cin2, int ks, Plan* pl) {
+    if (cout <= 0 || cin1 <= 0 || cin2 < 0 || (ks != 1 && ks != 3)) return UAPS_EINVAL;
+    pl->nseg = cin2 > 0 ? 2 : 1;
+    pl->seg_pad[0] = (cin1 + 15) / 16 * 16;
+    pl->seg_pad[1] = (cin2 + 15) / 16 * 16;
+    int ck = pick_ck(pl->seg_pad[0]);
+    if (pl->nseg > 1) { const int ck2 = pick_ck(pl->seg_pad[1]); if (ck2 < ck) ck = ck2; }
+    pl->ck = ck;
+    pl->chunks[0] = pl->seg_pad[0] / ck;
+    pl->chunks[1] = pl->nseg > 1 ? pl->seg_pad[1] / ck : 0;
+    pl->n_tile = pick_n_tile(cout);
+    pl->n_tiles = (cout + pl->n_tile - 1) / pl->n_tile;
+    pl->iters = (pl->chunks[0] + pl->chunks[1]) * ks;
+    pl->packed_bytes = (size_t)pl->n_tiles * pl->iters * ks * pl->n_tile * ck * 2;
+    return UAPS_OK;
+}
+
+// cuTensorMapEncodeTiled is a driver-API symbol; it is resolved through the runtime at first use so the
+// library has no link-time dependency on libcuda (it must still dlopen on a box without a driver).
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int encode_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, int ck, int box_h) {
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (encode == nullptr) return UAPS_ENODEV;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)ck, (cuuint32_t)TILE_W, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? UAPS_OK : UAPS_EINVAL;
+}
+}  // namespace
+
+UAPS_API size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks) {
+    Plan pl;
+    if (make_plan(cout, cin1, cin2, ks, &pl) != UAPS_OK) return 0;
+    return pl.packed_bytes;
+}
+
+UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks, int transpose,
+                                    cudaStream_t stream) {
+    Plan pl;
+    int rc = make_plan(cout, cin1, cin2, ks, &pl);
+    if (rc != UAPS_OK) return rc;
+    if (w == nullptr || w_packed == nullptr) return UAPS_EINVAL;
+    if (!aligned_to(w_packed, 16)) return UAPS_EALIGN;
+    PackArgs p{};
+    p.w = w; p.dst = reinterpret_cast<unsigned char*>(w_packed);
+    p.cout = cout; p.cin_total = cin1 + cin2; p.ks = ks; p.n_tile = pl.n_tile; p.n_tiles = pl.n_tiles; p.ck = pl.ck;
+    p.nseg = pl.nseg; p.seg_c[0] = cin1; p.seg_c[1] = cin2; p.seg_pad[0] = pl.seg_pad[0]; p.seg_pad[1] = pl.seg_pad[1];
+    p.transpose = transpose;
+    const long long total = (long long)pl.packed_bytes / 16;
+    const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    pack_weights_kernel<<<grid, 256, 0, stream>>>(p);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}
+
+UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
+                             const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
+                             int cin1, int cin2, int cout, int ks, cudaStream_t stream) {
+    Plan pl;
+    int rc = make_plan(cout, cin1, cin2, ks, &pl);
+    if (rc != UAPS_OK) return rc;
+    if (x1 == nullptr || w_packed == nullptr || out == nullptr || B <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
+    if (cin2 > 0 && x2 == nullptr) return UAPS_EINVAL;
+    // the activation tensors must physically hold the zero-padded channel count (c*_stride), 16-byte aligned rows
+    if (c1_stride < pl.seg_pad[0] || (c1_stride % 8) != 0 || (cin2 > 0 && (c2_stride < pl.seg_pad[1] || (c2_stride % 8) != 0)))
+        return UAPS_ERANGE;
+    if (!aligned_to(x1, 16) || (x2 && !aligned_to(x2, 16)) || !aligned_to(out, 16) || !aligned_to(w_packed, 16)) return UAPS_EALIGN;
+    if (!out_nchw_f32 && (out_c_stride < cout || (out_c_stride % 8) != 0)) return UAPS_ERANGE;
+
+    ConvArgs a{};
+    a.B = B; a.H = H; a.W = W; a.cout = cout; a.cout_stride = out_c_stride; a.n_tile = pl.n_tile; a.nseg = pl.nseg;
+    a.chunks[0] = pl.chunks[0]; a.chunks[1] = pl.chunks[1]; a.ks = ks;
+    a.tiles_x = (W + TILE_W - 1) / TILE_W; a.tiles_y = (H + TILE_H - 1) / TILE_H;
+    a.out_nchw_f32 = out_nchw_f32; a.bias = bias; a.w_packed = reinterpret_cast<const unsigned char*>(w_packed); a.out = out;
+    const int row_bytes = pl.ck * 2;
+    const int a_bytes = (TILE_H + ks - 1) * TILE_W * row_bytes, b_bytes = ks * pl.n_tile * row_bytes;
+    const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
+    int stages = pl.iters < MAX_STAGES ? pl.iters : MAX_STAGES;
+    while (stages > 1 && (size_t)stages * stage_bytes > 200 * 1024) --stages;
+    a.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;            // + slack for the 1024-byte alignment
+
+    CUtensorMap m0, m1;
+    rc = encode_map(&m0, x1, B, H, W, c1_stride, pl.ck, TILE_H + ks - 1);
+    if (rc != UAPS_OK) return rc;
+    rc = encode_map(&m1, cin2 > 0 ? x2 : x1, B, H, W, cin2 > 0 ? c2_stride : c1_stride, pl.ck, TILE_H + ks - 1);
+    if (rc != UAPS_OK) return rc;
+
+    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)pl.n_tiles, 1);
+    cudaError_t e;
+#define UAPS_CONV_LAUNCH(CKV)                                                                                   \
+    e = cudaFuncSetAttribute(conv_igemm_kernel<CKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return (int)e;                                                                        \
+    conv_igemm_kernel<CKV><<<grid, THREADS, smem, stream>>>(m0, m1, a);
+    if (pl.ck == 64) { UAPS_CONV_LAUNCH(64) } else if (pl.ck == 32) { UAPS_CONV_LAUNCH(32) } else { UAPS_CONV_LAUNCH(16) }
+#undef UAPS_CONV_LAUNCH
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}
