@@ -284,7 +284,8 @@ def run_ours(args):
     train = None
     if not args.no_train_step:
         try:
-            train = train_step_bench(dev, group, world, rank)
+            train = train_step_bench(dev, group, world, rank, compute="bf16")
+            train["fp32_path"] = train_step_bench(dev, group, world, rank, compute="fp32")
         except Exception as e:
             train = {"error": repr(e)[:300]}
 
@@ -365,13 +366,13 @@ def loss_sweep(dev, lib, L, iters: int = 10):
     return out
 
 
-def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3):
+def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3, compute: str = "bf16"):
     """Secondary: full UAPS iteration at the NEU shape (3x256x256, C=4, K=4), TRAIN_B + TRAIN_B images per GPU."""
     import torch.distributed as dist
     from uaps_b200.train import UAPSTrainer
     from uaps_b200.unet import UNet_UAPS
     torch.manual_seed(1337)
-    model = UNet_UAPS(3, C).to(dev)
+    model = UNet_UAPS(3, C, compute=compute).to(dev)
     trainer = UAPSTrainer(model, group=group)
     gen = torch.Generator().manual_seed(1337 + rank)
     xl_h = torch.randn(TRAIN_B, 3, H, W, generator=gen).pin_memory()
@@ -403,7 +404,9 @@ def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3):
     ms = t.item() / steps
     return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "images_per_s": 2 * TRAIN_B * world * 1e3 / ms, "unit": "iters/s",
             "loss": float(loss_h), "config": f"UNet_UAPS 3x{H}x{W} C={C} K={K}, {TRAIN_B}+{TRAIN_B} images/GPU, "
-            f"dp{world}, host images in the timed region (e2e)", "convs": "cuDNN fp32 (interim; see DESIGN.md)"}
+            f"dp{world}, host images in the timed region (e2e)",
+            "convs": "tcgen05 implicit GEMM (fprop + dgrad), bf16 channels-last; wgrad/BN/pool/upsample via torch"
+            if compute == "bf16" else "cuDNN fp32 (reference-precision path)"}
 
 
 def main():

@@ -75,3 +75,61 @@ class PackedConv:
                                             out.data_ptr(), ocs, int(out_nchw_f32), B, H, W, self.cin1, self.cin2,
                                             self.cout, self.ks, L.stream_ptr()), "uaps_conv_fprop")
         return out
+
+
+# ---- autograd: conv layer of the bf16 path -------------------------------------------------------
+def _nhwc_view(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW channels_last bf16 tensor -> its [B,H,W,C] memory view (no copy)."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last), \
+        "bf16 path tensors are channels_last"
+    return x.permute(0, 2, 3, 1)
+
+
+def _as_cl(y_nhwc: torch.Tensor) -> torch.Tensor:
+    return y_nhwc.permute(0, 3, 1, 2)        # logical NCHW, channels_last memory
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = conv(cat([x1, x2]), W) + b on tcgen05; dX by the same kernel with the rotated/transposed
+    packing; dW and db by the library (cuDNN) -- the weight-gradient kernel is the next milestone."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias, nchw_f32_out):
+        co, ci, ks, _ = weight.shape
+        c1 = x1.shape[1]
+        split = None if x2 is None else c1
+        conv = PackedConv(weight, bias, cin_split=split)
+        y = conv(_nhwc_view(x1), None if x2 is None else _nhwc_view(x2), out_nchw_f32=nchw_f32_out)
+        ctx.save_for_backward(x1, x2, weight)
+        ctx.has_bias, ctx.nchw = bias is not None, nchw_f32_out
+        return y if nchw_f32_out else _as_cl(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x1, x2, weight = ctx.saved_tensors
+        co, ci, ks, _ = weight.shape
+        if ctx.nchw:                                         # fp32 NCHW logits gradient -> bf16 channels_last
+            gy = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        elif not gy.is_contiguous(memory_format=torch.channels_last):
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        gy_nhwc = gy.permute(0, 2, 3, 1)
+        if gy_nhwc.shape[-1] % 16:                            # pad the K segment to the kernel's granule
+            pad = torch.zeros((*gy_nhwc.shape[:3], pad16(co)), dtype=torch.bfloat16, device=gy.device)
+            pad[..., :co] = gy_nhwc
+            gy_nhwc = pad
+        # data gradient: tcgen05 kernel, W'[ci][co] rotated by 180 degrees
+        gx = PackedConv(weight, None, transpose=True)(gy_nhwc)          # [B,H,W,pad16(ci)]
+        c1 = x1.shape[1]
+        g1 = _as_cl(gx[..., :c1]) if ctx.needs_input_grad[0] else None
+        g2 = _as_cl(gx[..., c1:ci]) if (x2 is not None and ctx.needs_input_grad[1]) else None
+        # weight / bias gradient (library)
+        xin = x1 if x2 is None else torch.cat([x1, x2], dim=1)
+        wb = weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        _, gw, gb = torch.ops.aten.convolution_backward(
+            gy, xin[:, :ci], wb, [co] if ctx.has_bias else None, [1, 1], [ks // 2, ks // 2], [1, 1], False, [0, 0], 1,
+            [False, True, ctx.has_bias])
+        return g1, g2, gw.float(), (gb.float() if ctx.has_bias else None), None
+
+
+def conv_bf16(x1: torch.Tensor, weight: torch.Tensor, bias, x2: torch.Tensor = None, nchw_f32_out: bool = False):
+    return _ConvFn.apply(x1, x2, weight, bias, nchw_f32_out)

@@ -25,6 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import perturb as P
+from .conv import conv_bf16, pad16
 
 FT_CHNS = (16, 32, 64, 128, 256)            # UAPS_unet.py:212
 ENC_DROPOUT = (0.05, 0.1, 0.2, 0.3, 0.5)    # :214
@@ -62,11 +63,17 @@ def _decoder(class_num: int) -> nn.Module:
 
 
 class UNet_UAPS(nn.Module):
-    def __init__(self, in_chns: int, class_num: int, n_aux: int = 3):
+    def __init__(self, in_chns: int, class_num: int, n_aux: int = 3, compute: str = "fp32"):
         super().__init__()
         if not 0 <= n_aux <= 5:
             raise ValueError("n_aux must be in [0, 5]")
+        if compute not in ("fp32", "bf16"):
+            raise ValueError("compute must be 'fp32' or 'bf16'")
         self.in_chns, self.class_num, self.n_aux = in_chns, class_num, n_aux
+        # "fp32": every layer in fp32 NCHW (cuDNN convs) -- the reference-precision path, 1e-5 parity.
+        # "bf16": channels-last bf16 activations, convolutions (forward + data gradient) on the
+        #         hand-written tcgen05 implicit-GEMM kernel, fp32 master weights, 1e-2 parity.
+        self.compute = compute
         self.encoder = _encoder(in_chns)
         self.main_decoder = _decoder(class_num)
         for a in range(1, n_aux + 1):
@@ -104,6 +111,63 @@ class UNet_UAPS(nn.Module):
             x = self._block(x, up.conv, 0.0, None, None)
         return dec.out_conv(x)
 
+    # ---- bf16 / tcgen05 path ------------------------------------------------------------------
+    def _block16(self, x, blk, p_drop, keep, x2=None):
+        cc = blk.conv_conv
+        c0, b0, c4, b4 = (cc.get_submodule(n) for n in ("0", "1", "4", "5"))
+        y = F.leaky_relu(b0(conv_bf16(x, c0.weight, c0.bias, x2=x2)), 0.01)
+        if p_drop > 0.0 and self.training:
+            if keep is not None:
+                y = y * (keep.to(y.dtype) * (1.0 / (1.0 - p_drop)))
+            else:
+                y = F.dropout(y, p_drop, True)
+        return F.leaky_relu(b4(conv_bf16(y, c4.weight, c4.bias)), 0.01)
+
+    def _encode16(self, x, enc_keep):
+        B, C, H, W = x.shape
+        x16 = torch.zeros((B, pad16(C), H, W), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
+        x16[:, :C] = x
+        feats, cur = [], x16
+        for lvl in range(5):
+            if lvl == 0:
+                blk = self.encoder.in_conv
+            else:
+                cur = F.max_pool2d(cur, 2)
+                blk = self.encoder.get_submodule(f"down{lvl}").maxpool_conv.get_submodule("1")
+            cur = self._block16(cur, blk, ENC_DROPOUT[lvl], None if enc_keep is None else enc_keep[lvl])
+            feats.append(cur)
+        return feats
+
+    def _decode16(self, feats, dec):
+        x = feats[4]
+        for i in range(1, 5):
+            up = dec.get_submodule(f"up{i}")
+            x = conv_bf16(x, up.conv1x1.weight, up.conv1x1.bias)
+            x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+            x = self._block16(feats[4 - i], up.conv, 0.0, None, x2=x)           # concat as two K segments
+        return conv_bf16(x, dec.out_conv.weight, dec.out_conv.bias, nchw_f32_out=True)
+
+    def _forward16(self, x, rand):
+        feats = self._encode16(x, None if rand is None else rand["enc_keep"])
+        outs = [self._decode16(feats, self.main_decoder)]
+        for a in range(1, self.n_aux + 1):
+            kind = _AUX_KINDS[(a - 1) % 3]
+            pf = []
+            for lvl, f in enumerate(feats):
+                if kind == "noise":
+                    n = rand["noise"][lvl].to(f.dtype) if rand is not None else \
+                        (torch.rand(f.shape[1:], device=f.device, dtype=torch.float32) * 0.6 - 0.3).to(f.dtype)
+                    pf.append(f * n.unsqueeze(0) + f)
+                elif kind == "dropout":
+                    pf.append(f * (rand["aux2_keep"][lvl].to(f.dtype) * 2.0) if rand is not None else F.dropout(f, 0.5, True))
+                else:
+                    u = rand["u"][lvl] if rand is not None else float(P.generator.uniform(0.7, 0.9))
+                    att = f.float().mean(dim=1, keepdim=True)
+                    thr = att.flatten(1).max(dim=1)[0].view(-1, 1, 1, 1) * u
+                    pf.append(f * (att < thr).to(f.dtype))
+            outs.append(self._decode16(pf, self.get_submodule(f"aux_decoder{a}")))
+        return tuple(outs) if self.n_aux else outs[0]
+
     def decoders(self) -> List[nn.Module]:
         return [self.main_decoder] + [self.get_submodule(f"aux_decoder{a}") for a in range(1, self.n_aux + 1)]
 
@@ -113,6 +177,8 @@ class UNet_UAPS(nn.Module):
         {"enc_keep": 5 masks, "noise": 5 tensors [C_l,H_l,W_l], "aux2_keep": 5 masks, "u": 5 floats}."""
         if x.shape[-1] % 16 or x.shape[-2] % 16:
             raise RuntimeError("H and W must be multiples of 16 (four 2x poolings; the reference fails in torch.cat)")
+        if self.compute == "bf16":
+            return self._forward16(x, rand)
         feats = self.encode(x, None if rand is None else rand["enc_keep"])
         outs = [self.decode(feats, self.main_decoder)]
         if self.n_aux == 0:
