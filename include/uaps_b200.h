@@ -156,6 +156,47 @@ int uaps_perturb3_bwd(const float* g_noise, const float* g_drop, const float* g_
                       double p_drop, const float* attention, const uint32_t* smax_enc, float u,
                       float* dx, int B, int C, int64_t HW, cudaStream_t stream);
 
+/* Channels-last bf16 versions of the perturbations for the bf16 / tcgen05 model path: x is
+ * [B, HW, C] bf16, C in {8, 16, ..., 256} (power of two), HW * C / 8 a multiple of 32.  Philox only.
+ * Same three outputs as uaps_perturb3 (any may be NULL); the _bwd entry folds the three upstream
+ * gradients into dx through the regenerated masks. */
+int uaps_fdrop_stats_nhwc(const void* x, int B, int C, int64_t HW, float* attention,
+                          uint32_t* smax_enc, cudaStream_t stream);
+int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range, double p_drop,
+                       const float* attention, const uint32_t* smax_enc, float u,
+                       void* y_noise, void* y_drop, void* y_fdrop, int B, int C, int64_t HW,
+                       cudaStream_t stream);
+int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, const void* g_fdrop, uint64_t seed,
+                           float noise_range, double p_drop, const float* attention,
+                           const uint32_t* smax_enc, float u, void* dx, int B, int C, int64_t HW,
+                           cudaStream_t stream);
+
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (utilities/UAPS_unet.py:74-75) and
+ * nn.MaxPool2d(2) (:56) on channels-last bf16, C % 8 == 0.
+ * upsample: backward = 0: x [B,H,W,C] -> y [B,2H,2W,C]; backward = 1: x is the upstream gradient
+ *   [B,2H,2W,C] and y receives d input [B,H,W,C] (gather form, deterministic).  H, W = INPUT size.
+ * maxpool: gy == NULL: out [B,H/2,W/2,C] = max of 2x2 windows of x [B,H,W,C]; gy given: out = d x, the
+ *   gradient routed to the first maximum of each window (torch's tie rule). */
+int uaps_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, int backward, cudaStream_t stream);
+int uaps_maxpool2_nhwc(const void* x, const void* gy, void* out, int B, int H, int W, int C, cudaStream_t stream);
+
+/* Fused train-mode BatchNorm2d + LeakyReLU(slope) + Dropout(p) on channels-last bf16 activations
+ * (utilities/UAPS_unet.py:37-43: nn.BatchNorm2d -> nn.LeakyReLU() -> nn.Dropout(p)).  y: [npix, C] bf16,
+ * C a power of two in 8..256.  sum / sumsq: device fp64 [C], zeroed by the caller before _stats.
+ * _act normalises with the batch statistics, writes save_mean / save_rstd [C] and (if given) advances
+ * running_mean / running_var with `momentum` (unbiased variance), as torch does.  The backward entry
+ * recomputes the LeakyReLU sign and the Philox dropout mask from y and the seed; sum_g / sum_gx (fp64 [C],
+ * zeroed by the caller) return d(beta) and d(gamma). */
+int uaps_bn_stats_nhwc(const void* y, int64_t npix, int C, double* sum, double* sumsq, cudaStream_t stream);
+int uaps_bn_act_nhwc(const void* y, const double* sum, const double* sumsq, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float momentum,
+                     float eps, float slope, double p_drop, uint64_t seed, void* out,
+                     float* save_mean, float* save_rstd, int64_t npix, int C, cudaStream_t stream);
+int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float* gamma, const float* beta,
+                         const float* save_mean, const float* save_rstd, float slope, double p_drop,
+                         uint64_t seed, double* sum_g, double* sum_gx, void* dy, int64_t npix, int C,
+                         cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 / TMEM / TMA (3x3 pad 1 or 1x1, stride 1), bf16 operands, fp32
  * accumulation.  Replaces the cuDNN calls behind nn.Conv2d in utilities/UAPS_unet.py:36,41 (ConvBlock),

@@ -103,3 +103,44 @@ def test_philox_mode_statistics_and_replay():
     # stand-alone entry points draw the same stream as the fused kernel
     assert torch.equal(P.FeatureNoise()(x.detach(), seed=1234), yn.detach())
     assert torch.equal(P.Dropout(x.detach(), 0.5, seed=1234), yd.detach())
+
+
+@pytest.mark.parametrize("shape", [(4, 16, 64, 64), (2, 64, 32, 32), (2, 256, 16, 16), (2, 128, 15, 40)])
+def test_channels_last_bf16_kernel(shape):
+    """bf16 NHWC perturb3 (Philox): semantics against torch expressions built from its own outputs."""
+    from uaps_b200 import perturb as P
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(shape, generator=g).abs() + 0.5).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    u = 0.8
+    yn, yd, yf = P.perturb3_nhwc(x, seed=42, u=u)
+    assert yn.is_contiguous(memory_format=torch.channels_last) and yn.dtype == torch.bfloat16
+    xf = x.detach().float()
+    # FeatureNoise: y = x (1 + n), |n| <= 0.3, one n per (c,h,w) shared by the batch
+    n = yn.float() / xf - 1.0
+    assert n.abs().max().item() <= 0.3 + 2e-2
+    assert (n[0] - n[1]).abs().max().item() <= 2e-2                    # bf16 output rounding only
+    assert abs(n.mean().item()) < 2e-2 and n.std().item() == pytest.approx(0.3 / 3 ** 0.5, rel=0.1)
+    # Dropout p = 0.5: kept values doubled, about half kept, mask differs across samples
+    kept = yd.float() != 0
+    assert torch.equal(yd.float()[kept], (2 * xf)[kept])
+    assert kept.float().mean().item() == pytest.approx(0.5, abs=0.02)
+    assert not torch.equal(kept[0], kept[1])
+    # FeatureDropout: pixels whose channel mean reaches u * max are zeroed (threshold ties excluded)
+    att = xf.mean(1, keepdim=True)
+    thr = att.flatten(1).max(1)[0].view(-1, 1, 1, 1) * u
+    margin = (att - thr).abs() > 1e-3 * thr
+    expect = xf * (att < thr)
+    assert torch.equal((yf.float() * margin), (expect * margin))
+    # backward regenerates the same masks
+    cots = [torch.randn(shape, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(3)]
+    (yn * cots[0]).sum().backward(retain_graph=True)
+    gn = x.grad.float().clone(); x.grad = None
+    assert torch.allclose(gn, cots[0].float() * (1 + n), rtol=3e-2, atol=3e-2)
+    (yd * cots[1]).sum().backward(retain_graph=True)
+    gd = x.grad.float().clone(); x.grad = None
+    assert torch.allclose(gd, cots[1].float() * kept * 2, rtol=1e-2, atol=1e-2)
+    (yf * cots[2]).sum().backward()
+    gf = x.grad.float()
+    assert torch.equal(gf * margin, cots[2].float() * (att < thr) * margin)

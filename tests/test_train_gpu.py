@@ -56,3 +56,27 @@ def test_training_iteration_matches_oracle():
         agree += (torch.sign(d_ref) == torch.sign(d_new)).sum().item()
         total += d_ref.numel()
     assert agree / total > 0.995, agree / total
+
+
+def test_bf16_path_trains_like_fp32_path():
+    """Ten iterations from the same initial weights on the same fixed batch: the bf16 / tcgen05 path's loss
+    curve tracks the fp32 path's (within 5% at every step) and both decrease."""
+    from uaps_b200 import perturb as P
+    from uaps_b200.train import UAPSTrainer
+    from uaps_b200.unet import UNet_UAPS
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(4)
+    xl, xu = torch.randn(4, 3, 64, 64, generator=g).to(dev), torch.randn(4, 3, 64, 64, generator=g).to(dev)
+    yl = (xl[:, 0] > 0).long() + 2 * (xl[:, 1] > 0).long()          # a learnable 4-class target
+    curves = {}
+    for mode in ("fp32", "bf16"):
+        torch.manual_seed(0)
+        P.manual_seed(1)
+        model = UNet_UAPS(3, 4, compute=mode).to(dev)
+        tr = UAPSTrainer(model)
+        curves[mode] = [tr.step(xl, yl, xu)["loss"].item() for _ in range(10)]
+    a, b = curves["fp32"], curves["bf16"]
+    assert a[-1] < 0.9 * a[0] and b[-1] < 0.9 * b[0], (a, b)
+    for s, (u, v) in enumerate(zip(a, b)):
+        assert abs(u - v) <= 0.05 * abs(u), (s, u, v)

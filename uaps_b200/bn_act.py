@@ -1,0 +1,66 @@
+"""Fused train-mode BatchNorm2d + LeakyReLU + Dropout on channels-last bf16 activations
+(utilities/UAPS_unet.py:37-43), over uaps_bn_* of the C ABI.  Saves only the conv output and the
+batch mean / rstd for backward; the LeakyReLU sign and the dropout mask are recomputed."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .perturb import _next_seed
+
+
+class _BnActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, slope, p_drop, seed):
+        L.require_cuda(y)
+        if y.dtype != torch.bfloat16 or not y.is_contiguous(memory_format=torch.channels_last):
+            raise RuntimeError("bn_act expects a channels_last bf16 [B,C,H,W] tensor")
+        B, C, H, W = y.shape
+        npix = B * H * W
+        dev = y.device
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        stats = torch.empty(2 * C, dtype=torch.float32, device=dev)          # save_mean | save_rstd
+        out = torch.empty_like(y)
+        lib = L.lib()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        with torch.cuda.device(dev):
+            L.check(lib.uaps_bn_stats_nhwc(y.data_ptr(), npix, C, sums.data_ptr(), sums[C:].data_ptr(), L.stream_ptr()),
+                    "uaps_bn_stats_nhwc")
+            L.check(lib.uaps_bn_act_nhwc(y.data_ptr(), sums.data_ptr(), sums[C:].data_ptr(), g32.data_ptr(), b32.data_ptr(),
+                                         None if running_mean is None else running_mean.data_ptr(),
+                                         None if running_var is None else running_var.data_ptr(),
+                                         momentum, eps, slope, p_drop, seed, out.data_ptr(), stats.data_ptr(),
+                                         stats[C:].data_ptr(), npix, C, L.stream_ptr()), "uaps_bn_act_nhwc")
+        ctx.save_for_backward(y, g32, b32, stats)
+        ctx.cfg = (slope, p_drop, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, g32, b32, stats = ctx.saved_tensors
+        slope, p_drop, seed = ctx.cfg
+        B, C, H, W = y.shape
+        g = g.contiguous(memory_format=torch.channels_last)
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=y.device)
+        dy = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            L.check(L.lib().uaps_bn_act_bwd_nhwc(g.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), stats.data_ptr(),
+                                                 stats[C:].data_ptr(), slope, p_drop, seed, sums.data_ptr(),
+                                                 sums[C:].data_ptr(), dy.data_ptr(), B * H * W, C, L.stream_ptr()),
+                    "uaps_bn_act_bwd_nhwc")
+        return dy, sums[C:].float(), sums[:C].float(), None, None, None, None, None, None, None
+
+
+def bn_lrelu_dropout(y: torch.Tensor, bn: torch.nn.BatchNorm2d, p_drop: float = 0.0, slope: float = 0.01,
+                     seed=None) -> torch.Tensor:
+    """dropout(leaky_relu(batch_norm(y))) with batch statistics; advances bn's running statistics like
+    nn.BatchNorm2d in training mode."""
+    if p_drop > 0.0 and seed is None:
+        seed = _next_seed()
+    out = _BnActFn.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum), float(bn.eps),
+                         float(slope), float(p_drop), 0 if seed is None else int(seed))
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return out

@@ -89,6 +89,40 @@ def _as_cl(y_nhwc: torch.Tensor) -> torch.Tensor:
     return y_nhwc.permute(0, 3, 1, 2)        # logical NCHW, channels_last memory
 
 
+_pack_cache = {}
+_scope_depth = 0
+
+
+class pack_scope:
+    """Within this scope (one training iteration: both forwards and the backward) a parameter is packed
+    once per layout instead of once per call.  The cache is dropped when the scope exits, i.e. before the
+    optimizer changes the weights -- fused optimizers update parameters in place WITHOUT bumping
+    ``Tensor._version``, so a version-keyed cache across steps would silently go stale."""
+
+    def __enter__(self):
+        global _scope_depth
+        _scope_depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _scope_depth
+        _scope_depth -= 1
+        if _scope_depth == 0:
+            _pack_cache.clear()
+        return False
+
+
+def packed(weight: torch.Tensor, bias, cin_split=None, transpose: bool = False) -> "PackedConv":
+    if _scope_depth == 0:
+        return PackedConv(weight, bias, cin_split=cin_split, transpose=transpose)
+    key = (id(weight), transpose, cin_split)
+    hit = _pack_cache.get(key)
+    if hit is None:
+        hit = PackedConv(weight, bias, cin_split=cin_split, transpose=transpose)
+        _pack_cache[key] = hit
+    return hit
+
+
 class _ConvFn(torch.autograd.Function):
     """y = conv(cat([x1, x2]), W) + b on tcgen05; dX by the same kernel with the rotated/transposed
     packing; dW and db by the library (cuDNN) -- the weight-gradient kernel is the next milestone."""
@@ -98,7 +132,7 @@ class _ConvFn(torch.autograd.Function):
         co, ci, ks, _ = weight.shape
         c1 = x1.shape[1]
         split = None if x2 is None else c1
-        conv = PackedConv(weight, bias, cin_split=split)
+        conv = packed(weight, bias, cin_split=split)
         y = conv(_nhwc_view(x1), None if x2 is None else _nhwc_view(x2), out_nchw_f32=nchw_f32_out)
         ctx.save_for_backward(x1, x2, weight)
         ctx.has_bias, ctx.nchw = bias is not None, nchw_f32_out
@@ -118,7 +152,7 @@ class _ConvFn(torch.autograd.Function):
             pad[..., :co] = gy_nhwc
             gy_nhwc = pad
         # data gradient: tcgen05 kernel, W'[ci][co] rotated by 180 degrees
-        gx = PackedConv(weight, None, transpose=True)(gy_nhwc)          # [B,H,W,pad16(ci)]
+        gx = packed(weight, None, transpose=True)(gy_nhwc)              # [B,H,W,pad16(ci)]
         c1 = x1.shape[1]
         g1 = _as_cl(gx[..., :c1]) if ctx.needs_input_grad[0] else None
         g2 = _as_cl(gx[..., c1:ci]) if (x2 is not None and ctx.needs_input_grad[1]) else None

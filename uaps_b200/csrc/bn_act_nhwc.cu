@@ -1,0 +1,263 @@
+// Fused train-mode BatchNorm2d + LeakyReLU(0.01) + Dropout(p) for the channels-last bf16 path:
+// the "BN -> LeakyReLU -> Dropout" run between the two convolutions of every ConvBlock
+// (utilities/UAPS_unet.py:37-43; batch statistics, eps 1e-5, momentum 0.1).
+//
+// The reference runs batch_norm (stats + transform), leaky_relu and dropout as separate ATen kernels,
+// forward and backward: ten HBM round trips per block.  Here:
+//   forward : bn_stats (read y) -> bn_act (read y, write a)                       2 + 4 B/element (bf16)
+//   backward: bn_act_bwd_reduce (read g, y) -> bn_act_bwd (read g, y, write dy)   4 + 6 B/element
+// The LeakyReLU sign and the dropout mask are recomputed in the backward pass from the saved conv
+// output y and a Philox counter, so neither the activation nor a mask is stored.
+//
+// Layout: y is [npix, C] bf16, C a power of two in 8..256.  G = C/8 adjacent threads own the eight
+// 16-byte chunks of a pixel; a thread's channels are fixed over its grid-stride loop, so per-channel
+// sums are private registers until one shared-memory + one fp64 global atomic per channel per CTA.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace uaps {
+namespace {
+
+constexpr int BT = 256;
+constexpr uint32_t kStreamBnDrop = 21;
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return r;
+}
+__device__ __forceinline__ void keep8(uint64_t seed, uint64_t idx, float p, float (&k)[8]) {
+    uint32_t r[4];
+    Philox::draw4(seed, idx, kStreamBnDrop, r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k[2 * i] = ((float)(r[i] & 0xffffu) * (1.0f / 65536.0f) >= p) ? 1.f : 0.f;
+        k[2 * i + 1] = ((float)(r[i] >> 16) * (1.0f / 65536.0f) >= p) ? 1.f : 0.f;
+    }
+}
+
+// two per-channel sums of a CTA -> fp64 global accumulators.  Lanes that own the same channel chunk
+// (lane % G) are folded by xor-shuffles first, so shared memory sees one atomic per warp per channel
+// and global memory one fp64 atomic per CTA per channel.
+__device__ __forceinline__ void cta_accumulate(float (&a)[8], float (&b)[8], int G, float* s_a, float* s_b,
+                                               double* g_a, double* g_b) {
+    const int C = 8 * G;
+    for (int c = threadIdx.x; c < C; c += BT) { s_a[c] = 0.f; s_b[c] = 0.f; }
+    __syncthreads();
+    for (int o = G; o < kWarp; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+            b[i] += __shfl_xor_sync(0xffffffffu, b[i], o);
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    if (lane < G) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { atomicAdd(s_a + lane * 8 + i, a[i]); atomicAdd(s_b + lane * 8 + i, b[i]); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += BT) { atomicAdd(g_a + c, (double)s_a[c]); atomicAdd(g_b + c, (double)s_b[c]); }
+}
+
+__global__ void __launch_bounds__(BT) bn_stats_kernel(const uint4* __restrict__ y, long long npix, int G,
+                                                      double* __restrict__ sum, double* __restrict__ sumsq) {
+    __shared__ float s_a[256], s_b[256];
+    const long long total = npix * G;
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < total; t += (long long)gridDim.x * BT) {
+        float v[8];
+        unpack8(__ldg(y + t), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] += v[i]; b[i] = fmaf(v[i], v[i], b[i]); }
+    }
+    cta_accumulate(a, b, G, s_a, s_b, sum, sumsq);
+}
+
+struct BnParams {
+    const double* sum; const double* sumsq;       // forward: batch sums; backward: sum(g'), sum(g' * xhat)
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var;      // updated by CTA 0 in forward (nullable)
+    float* save_mean; float* save_rstd;           // forward: written by CTA 0; backward: read
+    float momentum, eps, slope, p, keep_scale;
+    uint64_t seed;
+    long long npix;
+    int G;
+};
+
+// forward: a = dropout(leaky_relu(gamma * (y - mean) * rstd + beta))
+__global__ void __launch_bounds__(BT) bn_act_kernel(const uint4* __restrict__ y, uint4* __restrict__ out, const BnParams p) {
+    __shared__ float s_scale[256], s_shift[256];
+    const int C = 8 * p.G;
+    const double n = (double)p.npix;
+    for (int c = threadIdx.x; c < C; c += BT) {
+        const double mean = p.sum[c] / n;
+        double var = p.sumsq[c] / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+        s_scale[c] = p.gamma[c] * rstd;
+        s_shift[c] = p.beta[c] - (float)mean * p.gamma[c] * rstd;
+        if (blockIdx.x == 0) {
+            p.save_mean[c] = (float)mean;
+            p.save_rstd[c] = rstd;
+            if (p.running_mean != nullptr) {
+                const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+                p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+                p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)unbiased;
+            }
+        }
+    }
+    __syncthreads();
+    const int chunk = threadIdx.x % p.G;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = s_scale[chunk * 8 + i]; sh[i] = s_shift[chunk * 8 + i]; }
+    const long long total = p.npix * p.G;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < total; t += (long long)gridDim.x * BT) {
+        float v[8], k[8];
+        unpack8(__ldg(y + t), v);
+        if (p.p > 0.f) keep8(p.seed, (uint64_t)t, p.p, k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float z = fmaf(v[i], sc[i], sh[i]);
+            z = z > 0.f ? z : z * p.slope;
+            if (p.p > 0.f) z *= k[i] * p.keep_scale;
+            v[i] = z;
+        }
+        out[t] = pack8(v);
+    }
+}
+
+// g' = g * dropout' * leaky_relu'(z); accumulate sum(g') and sum(g' * xhat) per channel
+__global__ void __launch_bounds__(BT) bn_act_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                                                               const BnParams p, double* __restrict__ sum_g,
+                                                               double* __restrict__ sum_gx) {
+    __shared__ float s_a[256], s_b[256];
+    const int chunk = threadIdx.x % p.G;
+    float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = chunk * 8 + i;
+        mean[i] = p.save_mean[c]; rstd[i] = p.save_rstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c];
+    }
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+    const long long total = p.npix * p.G;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < total; t += (long long)gridDim.x * BT) {
+        float gv[8], v[8], k[8];
+        unpack8(__ldg(g + t), gv);
+        unpack8(__ldg(y + t), v);
+        if (p.p > 0.f) keep8(p.seed, (uint64_t)t, p.p, k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float xh = (v[i] - mean[i]) * rstd[i];
+            const float z = fmaf(ga[i], xh, be[i]);
+            float gp = gv[i] * (z > 0.f ? 1.f : p.slope);
+            if (p.p > 0.f) gp *= k[i] * p.keep_scale;
+            a[i] += gp;
+            b[i] = fmaf(gp, xh, b[i]);
+        }
+    }
+    cta_accumulate(a, b, p.G, s_a, s_b, sum_g, sum_gx);
+}
+
+// dy = gamma * rstd * (g' - mean(g') - xhat * mean(g' * xhat))
+__global__ void __launch_bounds__(BT) bn_act_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                                                        uint4* __restrict__ dy, const BnParams p) {
+    const int chunk = threadIdx.x % p.G;
+    const float invn = (float)(1.0 / (double)p.npix);
+    float mean[8], rstd[8], ga[8], be[8], mg[8], mgx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = chunk * 8 + i;
+        mean[i] = p.save_mean[c]; rstd[i] = p.save_rstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c];
+        mg[i] = (float)p.sum[c] * invn; mgx[i] = (float)p.sumsq[c] * invn;
+    }
+    const long long total = p.npix * p.G;
+    for (long long t = (long long)blockIdx.x * BT + threadIdx.x; t < total; t += (long long)gridDim.x * BT) {
+        float gv[8], v[8], k[8];
+        unpack8(__ldg(g + t), gv);
+        unpack8(__ldg(y + t), v);
+        if (p.p > 0.f) keep8(p.seed, (uint64_t)t, p.p, k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float xh = (v[i] - mean[i]) * rstd[i];
+            const float z = fmaf(ga[i], xh, be[i]);
+            float gp = gv[i] * (z > 0.f ? 1.f : p.slope);
+            if (p.p > 0.f) gp *= k[i] * p.keep_scale;
+            v[i] = ga[i] * rstd[i] * (gp - mg[i] - xh * mgx[i]);
+        }
+        dy[t] = pack8(v);
+    }
+}
+
+inline int bn_grid(long long chunks, int ctas_per_sm = 8) {
+    long long want = ceil_div<long long>(chunks, BT), cap = (long long)device_info().sm_count * ctas_per_sm;
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+inline bool valid_c(int C) { const int G = C / 8; return C % 8 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0; }
+
+}  // namespace
+}  // namespace uaps
+
+using namespace uaps;
+
+UAPS_API int uaps_bn_stats_nhwc(const void* y, int64_t npix, int C, double* sum, double* sumsq, cudaStream_t stream) {
+    if (y == nullptr || sum == nullptr || sumsq == nullptr || npix <= 0) return UAPS_EINVAL;
+    if (!valid_c(C)) return UAPS_ERANGE;
+    if (!aligned_to(y, 16) || !aligned_to(sum, 8) || !aligned_to(sumsq, 8)) return UAPS_EALIGN;
+    bn_stats_kernel<<<bn_grid(npix * (C / 8), 4), BT, 0, stream>>>(reinterpret_cast<const uint4*>(y), npix, C / 8, sum, sumsq);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}
+
+UAPS_API int uaps_bn_act_nhwc(const void* y, const double* sum, const double* sumsq, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, float momentum, float eps, float slope, double p_drop,
+                              uint64_t seed, void* out, float* save_mean, float* save_rstd, int64_t npix, int C,
+                              cudaStream_t stream) {
+    if (y == nullptr || sum == nullptr || sumsq == nullptr || gamma == nullptr || beta == nullptr || out == nullptr ||
+        save_mean == nullptr || save_rstd == nullptr || npix <= 0)
+        return UAPS_EINVAL;
+    if (!valid_c(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
+    if (!aligned_to(y, 16) || !aligned_to(out, 16)) return UAPS_EALIGN;
+    BnParams p{};
+    p.sum = sum; p.sumsq = sumsq; p.gamma = gamma; p.beta = beta; p.running_mean = running_mean; p.running_var = running_var;
+    p.save_mean = save_mean; p.save_rstd = save_rstd; p.momentum = momentum; p.eps = eps; p.slope = slope; p.p = (float)p_drop;
+    p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
+    bn_act_kernel<<<bn_grid(npix * (C / 8)), BT, 0, stream>>>(reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(out), p);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}
+
+UAPS_API int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float* gamma, const float* beta, const float* save_mean,
+                                  const float* save_rstd, float slope, double p_drop, uint64_t seed, double* sum_g,
+                                  double* sum_gx, void* dy, int64_t npix, int C, cudaStream_t stream) {
+    if (g_out == nullptr || y == nullptr || gamma == nullptr || beta == nullptr || save_mean == nullptr || save_rstd == nullptr ||
+        sum_g == nullptr || sum_gx == nullptr || dy == nullptr || npix <= 0)
+        return UAPS_EINVAL;
+    if (!valid_c(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
+    if (!aligned_to(g_out, 16) || !aligned_to(y, 16) || !aligned_to(dy, 16)) return UAPS_EALIGN;
+    BnParams p{};
+    p.sum = sum_g; p.sumsq = sum_gx; p.gamma = gamma; p.beta = beta; p.save_mean = const_cast<float*>(save_mean);
+    p.save_rstd = const_cast<float*>(save_rstd); p.slope = slope; p.p = (float)p_drop;
+    p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
+    const int grid = bn_grid(npix * (C / 8));
+    // sum_g / sum_gx (zeroed by the caller) receive sum(g') and sum(g' * xhat) = d beta and d gamma
+    bn_act_bwd_reduce_kernel<<<bn_grid(npix * (C / 8), 4), BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y), p,
+                                                     sum_g, sum_gx);
+    UAPS_LAUNCH_CHECK();
+    bn_act_bwd_kernel<<<grid, BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y),
+                                              reinterpret_cast<uint4*>(dy), p);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}

@@ -1,0 +1,191 @@
+// Bilinear x2 upsampling with align_corners=True (nn.Upsample in UpBlock, utilities/UAPS_unet.py:74-75,84)
+// and 2x2 max pooling (nn.MaxPool2d(2) in DownBlock, :56) on channels-last bf16 activations, forward and
+// backward.  One thread owns a 16-byte chunk (8 channels) of one OUTPUT pixel (forward) or one INPUT
+// pixel (backward: gather form, no atomics), so every access is a full 16-byte vector and a warp
+// covers 512 contiguous bytes.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace uaps {
+namespace {
+
+constexpr int RT = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return r;
+}
+
+// source coordinate of output index o: o * (in-1)/(out-1)  (align_corners=True), as torch computes it in fp32
+__device__ __forceinline__ void src_coord(int o, float scale, int in_size, int& i0, int& i1, float& l1) {
+    const float s = scale * o;
+    i0 = (int)s;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(RT) upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H,
+                                                            int W, int G, float sh, float sw) {
+    const int OH = 2 * H, OW = 2 * W;
+    const long long total = (long long)B * OH * OW * G;
+    for (long long t = (long long)blockIdx.x * RT + threadIdx.x; t < total; t += (long long)gridDim.x * RT) {
+        const int g = (int)(t % G);
+        long long p = t / G;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH);
+        const int b = (int)(p / OH);
+        int y0, y1, x0, x1; float ly, lx;
+        src_coord(oy, sh, H, y0, y1, ly);
+        src_coord(ox, sw, W, x0, x1, lx);
+        const uint4* xb = x + (size_t)b * H * W * G;
+        float a[8], c[8], d[8], e[8], o[8];
+        unpack8(__ldg(xb + ((size_t)y0 * W + x0) * G + g), a);
+        unpack8(__ldg(xb + ((size_t)y0 * W + x1) * G + g), c);
+        unpack8(__ldg(xb + ((size_t)y1 * W + x0) * G + g), d);
+        unpack8(__ldg(xb + ((size_t)y1 * W + x1) * G + g), e);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * c[i]) + ly * (hx * d[i] + lx * e[i]);
+        y[t] = pack8(o);
+    }
+}
+
+// gather backward: input pixel (iy, ix) collects from the <= 3 x 3 output pixels whose stencil touches it
+__global__ void __launch_bounds__(RT) upsample2x_bwd_kernel(const uint4* __restrict__ gy, uint4* __restrict__ gx, int B, int H,
+                                                            int W, int G, float sh, float sw) {
+    const int OH = 2 * H, OW = 2 * W;
+    const long long total = (long long)B * H * W * G;
+    for (long long t = (long long)blockIdx.x * RT + threadIdx.x; t < total; t += (long long)gridDim.x * RT) {
+        const int g = (int)(t % G);
+        long long p = t / G;
+        const int ix = (int)(p % W); p /= W;
+        const int iy = (int)(p % H);
+        const int b = (int)(p / H);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        // candidate outputs: o with floor(scale*o) in {i-1, i}; 1/scale = 2 + 1/(in-1) <= 3 -> o in [2i-4, 2i+4]
+        const int oy_lo = max(0, 2 * iy - 4), oy_hi = min(OH - 1, 2 * iy + 4);
+        const int ox_lo = max(0, 2 * ix - 4), ox_hi = min(OW - 1, 2 * ix + 4);
+        const uint4* gb = gy + (size_t)b * OH * OW * G;
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            int y0, y1; float ly;
+            src_coord(oy, sh, H, y0, y1, ly);
+            const float wy = (y0 == iy ? 1.f - ly : 0.f) + (y1 == iy ? ly : 0.f);
+            if (wy == 0.f) continue;
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                int x0, x1; float lx;
+                src_coord(ox, sw, W, x0, x1, lx);
+                const float wx = (x0 == ix ? 1.f - lx : 0.f) + (x1 == ix ? lx : 0.f);
+                if (wx == 0.f) continue;
+                float v[8];
+                unpack8(__ldg(gb + ((size_t)oy * OW + ox) * G + g), v);
+                const float w = wy * wx;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+            }
+        }
+        gx[t] = pack8(acc);
+    }
+}
+
+__global__ void __launch_bounds__(RT) maxpool2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int G) {
+    const int OH = H / 2, OW = W / 2;
+    const long long total = (long long)B * OH * OW * G;
+    for (long long t = (long long)blockIdx.x * RT + threadIdx.x; t < total; t += (long long)gridDim.x * RT) {
+        const int g = (int)(t % G);
+        long long p = t / G;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH);
+        const int b = (int)(p / OH);
+        const uint4* xb = x + ((size_t)b * H * W + (size_t)(2 * oy) * W + 2 * ox) * G + g;
+        float a[8], c[8], d[8], e[8];
+        unpack8(__ldg(xb), a); unpack8(__ldg(xb + G), c);
+        unpack8(__ldg(xb + (size_t)W * G), d); unpack8(__ldg(xb + (size_t)W * G + G), e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaxf(fmaxf(a[i], c[i]), fmaxf(d[i], e[i]));
+        y[t] = pack8(a);
+    }
+}
+
+// the gradient goes to the first maximum of the window in (row, column) order, as torch's max_pool2d backward does
+__global__ void __launch_bounds__(RT) maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gy,
+                                                          uint4* __restrict__ gx, int B, int H, int W, int G) {
+    const int OH = H / 2, OW = W / 2;
+    const long long total = (long long)B * OH * OW * G;
+    for (long long t = (long long)blockIdx.x * RT + threadIdx.x; t < total; t += (long long)gridDim.x * RT) {
+        const int g = (int)(t % G);
+        long long p = t / G;
+        const int ox = (int)(p % OW); p /= OW;
+        const int oy = (int)(p % OH);
+        const int b = (int)(p / OH);
+        const size_t base = ((size_t)b * H * W + (size_t)(2 * oy) * W + 2 * ox) * G + g;
+        const size_t offs[4] = {0, (size_t)G, (size_t)W * G, (size_t)W * G + G};
+        float v[4][8], gv[8], o[4][8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) unpack8(__ldg(x + base + offs[k]), v[k]);
+        unpack8(__ldg(gy + t), gv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int best = 0;
+            float m = v[0][i];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (v[k][i] > m) { m = v[k][i]; best = k; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k][i] = (k == best) ? gv[i] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gx[base + offs[k]] = pack8(o[k]);
+    }
+}
+
+inline int rgrid(long long n) {
+    long long want = ceil_div<long long>(n, RT), cap = (long long)device_info().sm_count * 8;
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace
+}  // namespace uaps
+
+using namespace uaps;
+
+UAPS_API int uaps_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, int backward, cudaStream_t stream) {
+    if (x == nullptr || y == nullptr || B <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
+    if (C % 8 != 0 || C <= 0) return UAPS_ERANGE;
+    if (!aligned_to(x, 16) || !aligned_to(y, 16)) return UAPS_EALIGN;
+    const int G = C / 8;
+    const float sh = H > 1 ? (float)(H - 1) / (float)(2 * H - 1) : 0.f, sw = W > 1 ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
+    if (!backward)      // x: [B,H,W,C] -> y: [B,2H,2W,C]
+        upsample2x_fwd_kernel<<<rgrid((long long)B * 4 * H * W * G), RT, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                                       reinterpret_cast<uint4*>(y), B, H, W, G, sh, sw);
+    else                // x: upstream gradient [B,2H,2W,C] -> y: [B,H,W,C]
+        upsample2x_bwd_kernel<<<rgrid((long long)B * H * W * G), RT, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                                   reinterpret_cast<uint4*>(y), B, H, W, G, sh, sw);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}
+
+UAPS_API int uaps_maxpool2_nhwc(const void* x, const void* gy, void* out, int B, int H, int W, int C, cudaStream_t stream) {
+    if (x == nullptr || out == nullptr || B <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
+    if (C % 8 != 0 || C <= 0 || (H % 2) != 0 || (W % 2) != 0) return UAPS_ERANGE;
+    if (!aligned_to(x, 16) || !aligned_to(out, 16) || !aligned_to(gy, 16)) return UAPS_EALIGN;
+    const int G = C / 8;
+    const long long n = (long long)B * (H / 2) * (W / 2) * G;
+    if (gy == nullptr)  // forward: x [B,H,W,C] -> out [B,H/2,W/2,C]
+        maxpool2_fwd_kernel<<<rgrid(n), RT, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H, W, G);
+    else                // backward: out = d x [B,H,W,C] (every element written)
+        maxpool2_bwd_kernel<<<rgrid(n), RT, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(gy),
+                                                         reinterpret_cast<uint4*>(out), B, H, W, G);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}

@@ -204,3 +204,50 @@ def perturb3(x: torch.Tensor, *, noise: Optional[torch.Tensor] = None, keep: Opt
     if u is None:
         u = float(generator.uniform(0.7, 0.9))
     return _Perturb3Fn.apply(x, noise, keep, int(seed), float(uniform_range), float(p), float(np.float32(u)))
+
+
+# ---- channels-last bf16 variant (bf16 / tcgen05 model path) ------------------------------------------
+class _Perturb3NhwcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, seed, rng, p, u):
+        L.require_cuda(x)
+        if x.dtype != torch.bfloat16 or not x.is_contiguous(memory_format=torch.channels_last):
+            raise RuntimeError("perturb3_nhwc expects a channels_last bf16 [B,C,H,W] tensor")
+        B, C, H, W = x.shape
+        attention = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
+        smax = torch.zeros(B, dtype=torch.int32, device=x.device)
+        ys = [torch.empty_like(x) for _ in range(3)]               # empty_like keeps channels_last
+        lib = L.lib()
+        with torch.cuda.device(x.device):
+            L.check(lib.uaps_fdrop_stats_nhwc(x.data_ptr(), B, C, H * W, attention.data_ptr(), smax.data_ptr(),
+                                              L.stream_ptr()), "uaps_fdrop_stats_nhwc")
+            L.check(lib.uaps_perturb3_nhwc(x.data_ptr(), seed, rng, p, attention.data_ptr(), smax.data_ptr(), u,
+                                           ys[0].data_ptr(), ys[1].data_ptr(), ys[2].data_ptr(), B, C, H * W,
+                                           L.stream_ptr()), "uaps_perturb3_nhwc")
+        ctx.save_for_backward(attention, smax)
+        ctx.args = (seed, rng, p, u)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, g_noise, g_drop, g_fdrop):
+        attention, smax = ctx.saved_tensors
+        seed, rng, p, u = ctx.args
+        gs = [None if g is None else g.contiguous(memory_format=torch.channels_last) for g in (g_noise, g_drop, g_fdrop)]
+        ref = next(g for g in gs if g is not None)
+        B, C, H, W = ref.shape
+        dx = torch.empty_like(ref)
+        with torch.cuda.device(ref.device):
+            L.check(L.lib().uaps_perturb3_nhwc_bwd(*[None if g is None else g.data_ptr() for g in gs], seed, rng, p,
+                                                   attention.data_ptr(), smax.data_ptr(), u, dx.data_ptr(), B, C, H * W,
+                                                   L.stream_ptr()), "uaps_perturb3_nhwc_bwd")
+        return dx, None, None, None, None
+
+
+def perturb3_nhwc(x: torch.Tensor, *, u: Optional[float] = None, seed: Optional[int] = None,
+                  uniform_range: float = 0.3, p: float = 0.5):
+    """Channels-last bf16 ``perturb3``: (FeatureNoise, Dropout, FeatureDropout) of one feature map in one pass."""
+    if seed is None:
+        seed = _next_seed()
+    if u is None:
+        u = float(generator.uniform(0.7, 0.9))
+    return _Perturb3NhwcFn.apply(x, int(seed), float(uniform_range), float(p), float(np.float32(u)))

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from .conv import pack_scope
 from .losses import uaps_supervised_loss, uaps_unlabeled_loss
 from .ramps import get_current_consistency_weight
 
@@ -79,16 +80,17 @@ class UAPSTrainer:
     def step(self, x_l: torch.Tensor, y_l: torch.Tensor, x_u: torch.Tensor,
              mix_w=None, rand_l=None, rand_u=None) -> Dict[str, torch.Tensor]:
         self.model.train()
-        out_l = self.model(x_l) if rand_l is None else self.model(x_l, rand=rand_l)         # :177
-        out_u = self.model(x_u) if rand_u is None else self.model(x_u, rand=rand_u)         # :185
-        sup, tce, tdice, ce_k = uaps_supervised_loss(out_l, y_l, group=self.group)           # :194-218
-        if mix_w is None:
-            mix_w = self.rng.dirichlet(np.ones(self.k))                                      # :251
-        cw1, cw2 = self.consistency_weights()                                                # :279-280
-        loss_u, ps_loss, l_unc, _, _ = uaps_unlabeled_loss(out_u, mix_w, cw1, cw2, group=self.group)  # :223-277
-        loss = sup + loss_u                                                                  # :282
-        self.grads.zero()                                                                    # :285
-        loss.backward()                                                                      # :287
+        with pack_scope():                                   # conv weights packed once for the whole iteration
+            out_l = self.model(x_l) if rand_l is None else self.model(x_l, rand=rand_l)         # :177
+            out_u = self.model(x_u) if rand_u is None else self.model(x_u, rand=rand_u)         # :185
+            sup, tce, tdice, ce_k = uaps_supervised_loss(out_l, y_l, group=self.group)           # :194-218
+            if mix_w is None:
+                mix_w = self.rng.dirichlet(np.ones(self.k))                                      # :251
+            cw1, cw2 = self.consistency_weights()                                                # :279-280
+            loss_u, ps_loss, l_unc, _, _ = uaps_unlabeled_loss(out_u, mix_w, cw1, cw2, group=self.group)  # :223-277
+            loss = sup + loss_u                                                                  # :282
+            self.grads.zero()                                                                    # :285
+            loss.backward()                                                                      # :287
         self.grads.all_reduce_sum(self.group)
         self.optimizer.step()                                                                # :292
         self.iter_num += 1

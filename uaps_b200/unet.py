@@ -25,7 +25,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import perturb as P
+from .bn_act import bn_lrelu_dropout
 from .conv import conv_bf16, pad16
+from .resample import maxpool2, upsample2x
 
 FT_CHNS = (16, 32, 64, 128, 256)            # UAPS_unet.py:212
 ENC_DROPOUT = (0.05, 0.1, 0.2, 0.3, 0.5)    # :214
@@ -115,12 +117,14 @@ class UNet_UAPS(nn.Module):
     def _block16(self, x, blk, p_drop, keep, x2=None):
         cc = blk.conv_conv
         c0, b0, c4, b4 = (cc.get_submodule(n) for n in ("0", "1", "4", "5"))
-        y = F.leaky_relu(b0(conv_bf16(x, c0.weight, c0.bias, x2=x2)), 0.01)
+        y = conv_bf16(x, c0.weight, c0.bias, x2=x2)
+        if self.training and keep is None:
+            # fused BN(batch stats) + LeakyReLU + Philox dropout: 2 kernels forward, 2 backward
+            y = bn_lrelu_dropout(y, b0, p_drop)
+            return bn_lrelu_dropout(conv_bf16(y, c4.weight, c4.bias), b4, 0.0)
+        y = F.leaky_relu(b0(y), 0.01)                         # eval mode / injected dropout mask (parity runs)
         if p_drop > 0.0 and self.training:
-            if keep is not None:
-                y = y * (keep.to(y.dtype) * (1.0 / (1.0 - p_drop)))
-            else:
-                y = F.dropout(y, p_drop, True)
+            y = y * (keep.to(y.dtype) * (1.0 / (1.0 - p_drop)))
         return F.leaky_relu(b4(conv_bf16(y, c4.weight, c4.bias)), 0.01)
 
     def _encode16(self, x, enc_keep):
@@ -132,7 +136,7 @@ class UNet_UAPS(nn.Module):
             if lvl == 0:
                 blk = self.encoder.in_conv
             else:
-                cur = F.max_pool2d(cur, 2)
+                cur = maxpool2(cur)
                 blk = self.encoder.get_submodule(f"down{lvl}").maxpool_conv.get_submodule("1")
             cur = self._block16(cur, blk, ENC_DROPOUT[lvl], None if enc_keep is None else enc_keep[lvl])
             feats.append(cur)
@@ -142,18 +146,23 @@ class UNet_UAPS(nn.Module):
         x = feats[4]
         for i in range(1, 5):
             up = dec.get_submodule(f"up{i}")
-            x = conv_bf16(x, up.conv1x1.weight, up.conv1x1.bias)
-            x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+            x = upsample2x(conv_bf16(x, up.conv1x1.weight, up.conv1x1.bias))
             x = self._block16(feats[4 - i], up.conv, 0.0, None, x2=x)           # concat as two K segments
         return conv_bf16(x, dec.out_conv.weight, dec.out_conv.bias, nchw_f32_out=True)
 
     def _forward16(self, x, rand):
         feats = self._encode16(x, None if rand is None else rand["enc_keep"])
         outs = [self._decode16(feats, self.main_decoder)]
+        fused = None
+        if rand is None and self.n_aux > 0:                    # one fused Philox kernel per level (rows a2-a4)
+            fused = [P.perturb3_nhwc(f) for f in feats]
         for a in range(1, self.n_aux + 1):
             kind = _AUX_KINDS[(a - 1) % 3]
+            if fused is not None and a <= 3:
+                outs.append(self._decode16([t[a - 1] for t in fused], self.get_submodule(f"aux_decoder{a}")))
+                continue
             pf = []
-            for lvl, f in enumerate(feats):
+            for lvl, f in enumerate(feats):                    # injected draws (parity runs) / 4th+ decoder: torch expressions
                 if kind == "noise":
                     n = rand["noise"][lvl].to(f.dtype) if rand is not None else \
                         (torch.rand(f.shape[1:], device=f.device, dtype=torch.float32) * 0.6 - 0.3).to(f.dtype)
