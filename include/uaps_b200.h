@@ -217,6 +217,14 @@ int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride
                     const float* bias, void* out, int out_c_stride, int out_nchw_f32,
                     int B, int H, int W, int cin1, int cin2, int cout, int ks, cudaStream_t stream);
 
+/* Weight gradient on tcgen05 (MN-major operands straight from the channels-last tensors):
+ * dw[co][ci_offset + ci][r][s] += sum_pixels dy[p][co] * x[p + (r-1, s-1)][ci].  dw is fp32 in torch layout
+ * [cout][cin_total][ks][ks] and is ACCUMULATED into (zero it first); a concatenated input is two calls
+ * with different ci_offset.  cin must be a multiple of 16 (pad the 3-channel network input). */
+int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int x_c_stride, float* dw,
+                    int B, int H, int W, int cout, int cin, int cin_total, int ci_offset, int ks,
+                    cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,3 +92,35 @@ def test_data_gradient_via_transposed_packing():
         F.conv2d(x, w.bfloat16().float(), padding=1).backward(dy.bfloat16().float())
         dx = from_nhwc(PackedConv(w, None, transpose=True)(to_nhwc_bf16(dy)), ci)
         assert (dx - x.grad).abs().max().item() <= 1e-2 * x.grad.abs().max().item(), (ci, co)
+
+
+@pytest.mark.parametrize("B,H,W,ci,co,ks", [
+    (2, 32, 32, 16, 16, 3), (2, 32, 32, 32, 32, 3), (2, 16, 16, 64, 64, 3), (1, 32, 32, 128, 128, 3),
+    (1, 16, 16, 256, 256, 3), (2, 32, 32, 32, 16, 1), (1, 16, 16, 256, 128, 1), (2, 64, 64, 16, 4, 3),
+    (1, 48, 40, 32, 64, 3), (1, 15, 40, 128, 128, 3), (4, 64, 64, 16, 32, 3),
+])
+def test_weight_gradient_matches_torch(B, H, W, ci, co, ks):
+    """tcgen05 wgrad (MN-major operands) vs autograd of torch's conv on the same bf16-rounded tensors."""
+    from uaps_b200.conv import conv_wgrad, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B + H + ci + 3 * co)
+    x = torch.randn(B, ci, H, W, generator=g).to(dev)
+    dy = torch.randn(B, co, H, W, generator=g).to(dev)
+    w = torch.zeros(co, ci, ks, ks, device=dev, requires_grad=True)
+    F.conv2d(x.bfloat16().float(), w, padding=ks // 2).backward(dy.bfloat16().float())
+    dw = conv_wgrad(to_nhwc_bf16(dy), [to_nhwc_bf16(x)], co, ci, ks)
+    err = (dw - w.grad).abs().max().item()
+    assert err <= 2e-3 * w.grad.abs().max().item(), (err, w.grad.abs().max().item())
+
+
+def test_weight_gradient_of_concat_input():
+    from uaps_b200.conv import conv_wgrad, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(12)
+    for c in (16, 64, 128):
+        skip, up = torch.randn(2, c, 32, 32, generator=g).to(dev), torch.randn(2, c, 32, 32, generator=g).to(dev)
+        dy = torch.randn(2, c, 32, 32, generator=g).to(dev)
+        w = torch.zeros(c, 2 * c, 3, 3, device=dev, requires_grad=True)
+        F.conv2d(torch.cat([skip, up], 1).bfloat16().float(), w, padding=1).backward(dy.bfloat16().float())
+        dw = conv_wgrad(to_nhwc_bf16(dy), [to_nhwc_bf16(skip), to_nhwc_bf16(up)], c, 2 * c, 3)
+        assert (dw - w.grad).abs().max().item() <= 2e-3 * w.grad.abs().max().item(), c

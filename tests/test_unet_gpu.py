@@ -90,7 +90,7 @@ def test_net_factory_and_input_check():
     assert len(out) == 4 and out[0].shape == (2, 2, 64, 96)
 
 
-def _torch_bf16_conv(x1, weight, bias, x2=None, nchw_f32_out=False):
+def _torch_bf16_conv(x1, weight, bias, x2=None, nchw_f32_out=False, bias_grad=True):
     """Test-side stand-in for uaps_b200.conv.conv_bf16: the same bf16 operands through cuDNN."""
     import torch.nn.functional as F
     xin = x1 if x2 is None else torch.cat([x1, x2], dim=1)

@@ -77,6 +77,21 @@ class PackedConv:
         return out
 
 
+def conv_wgrad(dy_nhwc: torch.Tensor, xs, cout: int, cin_total: int, ks: int) -> torch.Tensor:
+    """dW (fp32, torch layout [cout][cin_total][ks][ks]) of a conv whose input is the channel concat of `xs`
+    (NHWC bf16 tensors, each a multiple of 16 channels) and whose output gradient is dy_nhwc."""
+    B, H, W, dcs = dy_nhwc.shape
+    dw = torch.zeros((cout, cin_total, ks, ks), dtype=torch.float32, device=dy_nhwc.device)
+    off = 0
+    with torch.cuda.device(dy_nhwc.device):
+        for x in xs:
+            c = x.shape[3]
+            L.check(L.lib().uaps_conv_wgrad(dy_nhwc.data_ptr(), dcs, x.data_ptr(), c, dw.data_ptr(), B, H, W, cout, c,
+                                            cin_total, off, ks, L.stream_ptr()), "uaps_conv_wgrad")
+            off += c
+    return dw
+
+
 # ---- autograd: conv layer of the bf16 path -------------------------------------------------------
 def _nhwc_view(x: torch.Tensor) -> torch.Tensor:
     """Logical NCHW channels_last bf16 tensor -> its [B,H,W,C] memory view (no copy)."""
@@ -125,17 +140,17 @@ def packed(weight: torch.Tensor, bias, cin_split=None, transpose: bool = False) 
 
 class _ConvFn(torch.autograd.Function):
     """y = conv(cat([x1, x2]), W) + b on tcgen05; dX by the same kernel with the rotated/transposed
-    packing; dW and db by the library (cuDNN) -- the weight-gradient kernel is the next milestone."""
+    packing; dW by the tcgen05 weight-gradient kernel (conv_wgrad.cu)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, weight, bias, nchw_f32_out):
+    def forward(ctx, x1, x2, weight, bias, nchw_f32_out, bias_grad):
         co, ci, ks, _ = weight.shape
         c1 = x1.shape[1]
         split = None if x2 is None else c1
         conv = packed(weight, bias, cin_split=split)
         y = conv(_nhwc_view(x1), None if x2 is None else _nhwc_view(x2), out_nchw_f32=nchw_f32_out)
         ctx.save_for_backward(x1, x2, weight)
-        ctx.has_bias, ctx.nchw = bias is not None, nchw_f32_out
+        ctx.has_bias, ctx.nchw, ctx.bias_grad = bias is not None, nchw_f32_out, bias_grad
         return y if nchw_f32_out else _as_cl(y)
 
     @staticmethod
@@ -156,14 +171,22 @@ class _ConvFn(torch.autograd.Function):
         c1 = x1.shape[1]
         g1 = _as_cl(gx[..., :c1]) if ctx.needs_input_grad[0] else None
         g2 = _as_cl(gx[..., c1:ci]) if (x2 is not None and ctx.needs_input_grad[1]) else None
-        # weight / bias gradient (library)
-        xin = x1 if x2 is None else torch.cat([x1, x2], dim=1)
-        wb = weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        _, gw, gb = torch.ops.aten.convolution_backward(
-            gy, xin[:, :ci], wb, [co] if ctx.has_bias else None, [1, 1], [ks // 2, ks // 2], [1, 1], False, [0, 0], 1,
-            [False, True, ctx.has_bias])
-        return g1, g2, gw.float(), (gb.float() if ctx.has_bias else None), None
+        # weight gradient: tcgen05 kernel on the same channels-last tensors (MN-major operands, no transposes)
+        xs = [_nhwc_view(x1)] + ([] if x2 is None else [_nhwc_view(x2)])
+        cin_pad = sum(t.shape[3] for t in xs)                 # the 3-channel network input is stored 16-padded
+        gw = conv_wgrad(gy_nhwc, xs, co, cin_pad, ks)
+        if cin_pad != ci:
+            gw = gw[:, :ci].contiguous()
+        gb = None
+        if ctx.has_bias:
+            # a bias in front of train-mode BatchNorm has an analytically zero gradient; only conv1x1 /
+            # out_conv (bias_grad=True) need the reduction
+            gb = gy.float().sum(dim=(0, 2, 3)) if ctx.bias_grad else torch.zeros(co, dtype=torch.float32, device=gy.device)
+        return g1, g2, gw, gb, None, None
 
 
-def conv_bf16(x1: torch.Tensor, weight: torch.Tensor, bias, x2: torch.Tensor = None, nchw_f32_out: bool = False):
-    return _ConvFn.apply(x1, x2, weight, bias, nchw_f32_out)
+def conv_bf16(x1: torch.Tensor, weight: torch.Tensor, bias, x2: torch.Tensor = None, nchw_f32_out: bool = False,
+              bias_grad: bool = True):
+    """bias_grad=False: the conv feeds a train-mode BatchNorm, whose mean subtraction makes d loss / d bias
+    exactly zero -- the reduction is skipped and zeros are returned (the reference accumulates rounding noise)."""
+    return _ConvFn.apply(x1, x2, weight, bias, nchw_f32_out, bias_grad)

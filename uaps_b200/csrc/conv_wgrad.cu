@@ -1,0 +1,227 @@
+// Weight gradient of the 3x3 / 1x1 convolutions on tcgen05 (UAPS_train.py:287 `loss.backward()` through
+// the nn.Conv2d layers of utilities/UAPS_unet.py:36,41,73,138):
+//     dW[co][ci][r][s] = sum over pixels p of dY[p][co] * X[p + (r-1, s-1)][ci]
+// GEMM per tap: M = output channels, N = a 16/32-wide chunk of input channels, K = pixels.  Both
+// operands are channels-last, so the reduction dimension (pixels) is the OUTER one: they are fed to the
+// tensor core as MN-major operands straight from the TMA boxes, no transpose pass:
+//   A = dY tile  [128 px][64 ch] x 2 boxes (SWIZZLE_128B): M-major, 8 pixel rows per swizzle atom;
+//       channels beyond Cout are zero (TMA out-of-bounds fill / a zeroed second box).
+//   B = X halo tile [(16+2)*8 px][n_chunk ch] per horizontal tap s (SWIZZLE_64B / 32B): N-major; the three
+//       vertical taps r are the same tile read 8 pixel rows (= one atom) further down, as in the forward kernel.
+// The 9 tap accumulators (9 x n_chunk fp32 columns) stay in TMEM across all pixel tiles of the CTA
+// (split-K over CTAs), then are added to dW with fp32 reductions.
+#include "tc_common.cuh"
+
+namespace uaps {
+namespace wgrad {
+using namespace uaps::tc;
+
+constexpr int TILE_H = 16, TILE_W = 8, TILE_M = 128;
+constexpr int THREADS = 128;
+constexpr int STAGES = 3;
+constexpr int A_BOX_BYTES = 128 * 128;            // 128 pixels x 64 channels x 2 B
+
+struct WgradArgs {
+    int B, H, W;
+    int cout, cin_total, ci_offset;
+    int ks, n_chunk;
+    int tiles_x, tiles_y, tiles_total, tiles_per_cta;
+    int two_boxes;                                 // cout > 64: second 64-channel box carries data
+    float* dw;
+};
+
+// MN-major descriptors (cute::UMMA canonical forms, units of 16 bytes):
+//   SW128: ((8,n),(8,k)):((1,LBO),(8,SBO))   SW64: ((4,n),(8,k)):((1,LBO),(4,SBO))   SW32: ((2,n),(8,k)):((1,LBO),(2,SBO))
+// k rows are `span` bytes apart, 8 of them form an atom, SBO = 8 * span; LBO = distance between MN groups.
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t span, uint32_t lbo_bytes) {
+    const uint64_t layout = span == 128 ? 2 : (span == 64 ? 4 : 6);
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)(((8 * span) >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
+}
+// D = F32, A = B = BF16, both MN-major (bits 15, 16), N >> 3, M >> 4
+__device__ __forceinline__ uint32_t idesc_mn(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(THREADS)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ WgradArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int halo = a.ks - 1;
+    const int row_b = a.n_chunk * 2;                                  // 32 or 64 bytes per pixel row of B
+    const int b_box = (TILE_H + halo) * TILE_W * row_b;
+    const int a_bytes = 2 * A_BOX_BYTES;
+    const int stage_bytes = (a_bytes + a.ks * b_box + 1023) & ~1023;
+    const int ntaps = a.ks * a.ks;
+
+    const int split = blockIdx.x, nc = blockIdx.y, mt = blockIdx.z;
+    const int tile_lo = split * a.tiles_per_cta;
+    const int tile_hi = min(a.tiles_total, tile_lo + a.tiles_per_cta);
+    const int ntiles = tile_hi - tile_lo;
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < ntaps * a.n_chunk) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (!a.two_boxes) {                               // channels 64..127 of the M operand are zero for the whole kernel
+        for (int s = 0; s < STAGES; ++s) {
+            uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes + A_BOX_BYTES);
+            for (int i = threadIdx.x; i < A_BOX_BYTES / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (ntiles > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int it = 0; it < ntiles; ++it) {
+                    int t = tile_lo + it;
+                    const int tx = t % a.tiles_x; t /= a.tiles_x;
+                    const int ty = t % a.tiles_y; t /= a.tiles_y;
+                    const int x0 = tx * TILE_W, y0 = ty * TILE_H, n_img = t;
+                    const int st = it % STAGES;
+                    mbar_wait(empty_bar + st, ((it / STAGES) & 1) ^ 1);
+                    unsigned char* sa = smem + (size_t)st * stage_bytes;
+                    mbar_expect_tx(full_bar + st, (a.two_boxes ? 2 : 1) * A_BOX_BYTES + a.ks * b_box);
+                    tma_load_4d(sa, &map_dy, mt * 128, x0, y0, n_img, full_bar + st);
+                    if (a.two_boxes) tma_load_4d(sa + A_BOX_BYTES, &map_dy, mt * 128 + 64, x0, y0, n_img, full_bar + st);
+                    for (int s = 0; s < a.ks; ++s)
+                        tma_load_4d(sa + a_bytes + s * b_box, &map_x, nc * a.n_chunk, x0 + s - halo / 2, y0 - halo / 2, n_img,
+                                    full_bar + st);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = idesc_mn(a.n_chunk);
+                for (int it = 0; it < ntiles; ++it) {
+                    const int st = it % STAGES;
+                    mbar_wait(full_bar + st, (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+                    for (int r = 0; r < a.ks; ++r)
+                        for (int s = 0; s < a.ks; ++s) {
+                            const uint32_t d = tmem_d + (uint32_t)((r * a.ks + s) * a.n_chunk);
+#pragma unroll
+                            for (int kk = 0; kk < TILE_M / 16; ++kk) {            // 16 pixels per MMA
+                                const uint64_t ad = desc_mn(sa + kk * 16 * 128, 128, A_BOX_BYTES);
+                                const uint64_t bd = desc_mn(sb + s * b_box + (r * TILE_W + kk * 16) * row_b, row_b, 0);
+                                umma_bf16(d, ad, bd, idesc, (it | kk) != 0);
+                            }
+                        }
+                    umma_commit(empty_bar + st);
+                }
+                umma_commit(&done_bar);
+            }
+            __syncwarp();
+        }
+        // ---- epilogue: lane = output channel; 9 taps x n_chunk input channels -> fp32 reductions into dW
+        mbar_wait(&done_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int co = mt * 128 + warp * 32 + lane;
+        for (int tap = 0; tap < ntaps; ++tap) {
+            for (int j = 0; j < a.n_chunk / 16; ++j) {
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + tap * a.n_chunk + j * 16, v);
+                if (co < a.cout) {
+                    const int ci0 = a.ci_offset + nc * a.n_chunk + j * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        atomicAdd(a.dw + ((size_t)co * a.cin_total + ci0 + i) * ntaps + tap, v[i]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+}  // namespace wgrad
+}  // namespace uaps
+
+using namespace uaps;
+using namespace uaps::wgrad;
+
+namespace {
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+int encode(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cs, int box_c, int box_h) {
+    EncodeTiledFn f = encode_fn();
+    if (f == nullptr) return UAPS_ENODEV;
+    cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TILE_W, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    return f(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? UAPS_OK : UAPS_EINVAL;
+}
+}  // namespace
+
+// dy: [B,H,W,dy_c_stride] bf16 (channels >= cout must be zero or absent), x: [B,H,W,x_c_stride] bf16 holding `cin`
+// channels of one K segment; dw: fp32 [cout][cin_total][ks][ks], ACCUMULATED into (caller zeroes it), the
+// segment's channels start at ci_offset.
+UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int x_c_stride, float* dw, int B, int H, int W,
+                             int cout, int cin, int cin_total, int ci_offset, int ks, cudaStream_t stream) {
+    if (dy == nullptr || x == nullptr || dw == nullptr || B <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
+    if (cout <= 0 || cin <= 0 || (ks != 1 && ks != 3) || ci_offset < 0 || ci_offset + cin > cin_total) return UAPS_EINVAL;
+    if ((dy_c_stride % 8) != 0 || (x_c_stride % 8) != 0 || dy_c_stride < cout || x_c_stride < cin) return UAPS_ERANGE;
+    if (!aligned_to(dy, 16) || !aligned_to(x, 16) || !aligned_to(dw, 4)) return UAPS_EALIGN;
+    const int cin_pad = (cin + 15) / 16 * 16;
+    if (x_c_stride < cin_pad && (cin % 16) != 0) return UAPS_ERANGE;        // padded chunk must exist (zeros) in memory
+    WgradArgs a{};
+    a.B = B; a.H = H; a.W = W; a.cout = cout; a.cin_total = cin_total; a.ci_offset = ci_offset; a.ks = ks;
+    a.n_chunk = (cin_pad % 32 == 0) ? 32 : 16;
+    a.tiles_x = (W + TILE_W - 1) / TILE_W; a.tiles_y = (H + TILE_H - 1) / TILE_H;
+    a.tiles_total = a.tiles_x * a.tiles_y * B;
+    a.two_boxes = cout > 64;
+    a.dw = dw;
+    const int n_chunks = cin_pad / a.n_chunk, m_tiles = (cout + 127) / 128;
+    int splits = (2 * device_info().sm_count + n_chunks * m_tiles - 1) / (n_chunks * m_tiles);
+    if (splits > a.tiles_total) splits = a.tiles_total;
+    if (splits < 1) splits = 1;
+    a.tiles_per_cta = (a.tiles_total + splits - 1) / splits;
+    splits = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    // the epilogue writes only real input channels: a padded chunk's extra columns (ci >= cin) must be skipped
+    if (cin_pad != cin) return UAPS_ERANGE;                                  // callers pad Cin=3 layers on their side (see conv.py)
+    const int row_b = a.n_chunk * 2, b_box = (TILE_H + ks - 1) * TILE_W * row_b;
+    const size_t smem = (size_t)STAGES * ((2 * A_BOX_BYTES + ks * b_box + 1023) & ~1023) + 1024;
+    CUtensorMap mdy, mx;
+    int rc = encode(&mdy, dy, B, H, W, dy_c_stride, 64, TILE_H);
+    if (rc != UAPS_OK) return rc;
+    rc = encode(&mx, x, B, H, W, x_c_stride, a.n_chunk, TILE_H + ks - 1);
+    if (rc != UAPS_OK) return rc;
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)splits, (unsigned)n_chunks, (unsigned)m_tiles);
+    conv_wgrad_kernel<<<grid, THREADS, smem, stream>>>(mdy, mx, a);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}

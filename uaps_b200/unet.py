@@ -117,15 +117,15 @@ class UNet_UAPS(nn.Module):
     def _block16(self, x, blk, p_drop, keep, x2=None):
         cc = blk.conv_conv
         c0, b0, c4, b4 = (cc.get_submodule(n) for n in ("0", "1", "4", "5"))
-        y = conv_bf16(x, c0.weight, c0.bias, x2=x2)
+        y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=False)
         if self.training and keep is None:
             # fused BN(batch stats) + LeakyReLU + Philox dropout: 2 kernels forward, 2 backward
             y = bn_lrelu_dropout(y, b0, p_drop)
-            return bn_lrelu_dropout(conv_bf16(y, c4.weight, c4.bias), b4, 0.0)
+            return bn_lrelu_dropout(conv_bf16(y, c4.weight, c4.bias, bias_grad=False), b4, 0.0)
         y = F.leaky_relu(b0(y), 0.01)                         # eval mode / injected dropout mask (parity runs)
         if p_drop > 0.0 and self.training:
             y = y * (keep.to(y.dtype) * (1.0 / (1.0 - p_drop)))
-        return F.leaky_relu(b4(conv_bf16(y, c4.weight, c4.bias)), 0.01)
+        return F.leaky_relu(b4(conv_bf16(y, c4.weight, c4.bias, bias_grad=False)), 0.01)
 
     def _encode16(self, x, enc_keep):
         B, C, H, W = x.shape
