@@ -26,6 +26,7 @@
 // One output tile per CTA, 4 warps: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer
 // (warp 1 owns the TMEM allocation), all four warps = epilogue.  Small layers hide latency by many
 // co-resident CTAs (their stages are a few KB), big layers by the STAGES-deep ring inside the CTA.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace uaps {
@@ -46,6 +47,9 @@ struct ConvArgs {
     int stages;
     int tiles_x, tiles_y;
     int out_nchw_f32;    // 1: write fp32 NCHW (logits), 0: bf16 NHWC
+    int num_tiles;       // spatial tiles x n_tiles (persistent kernel)
+    int n_tiles;
+    int resident;        // 1: this layer's packed weights stay in shared memory for the whole kernel
     const float* bias;   // [>= n_tiles * n_tile] or null
     const unsigned char* w_packed;
     void* out;
@@ -187,6 +191,179 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
                 for (int i = 0; i < 16; ++i)
                     if (c0 + i < a.cout) o[i] = __float2bfloat16_rn(v[i]);
             }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// ---- v2: persistent, warp-specialised, TMEM double-buffered ---------------------------------------------
+// One CTA per SM slot loops over output tiles.  warp 0 = TMA producer (runs ahead across tile
+// boundaries through the shared-memory ring), warp 1 = MMA issuer (alternates between two TMEM
+// accumulators), warps 2-5 = epilogue (drain accumulator i while the MMAs of tile i+1 run).  Layers
+// whose packed weights fit in 64 KB keep them resident in shared memory: their stages carry only
+// activations, so a tile costs one A box per horizontal tap out of L2 and nothing else.
+constexpr int THREADS2 = 192;
+constexpr int W_RESIDENT_MAX = 64 * 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int CK>
+__global__ void __launch_bounds__(THREADS2)
+conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                             const __grid_constant__ ConvArgs a) {
+    constexpr int ROW_BYTES = CK * 2;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2], w_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int halo = a.ks - 1;
+    const int a_bytes = (TILE_H + halo) * TILE_W * ROW_BYTES;
+    const int b_bytes = a.ks * a.n_tile * ROW_BYTES;
+    const int iters = (a.chunks[0] + (a.nseg > 1 ? a.chunks[1] : 0)) * a.ks;
+    const int w_region = a.resident ? ((iters * b_bytes + 1023) & ~1023) : 0;
+    const int stage_bytes = (a_bytes + (a.resident ? 0 : b_bytes) + 1023) & ~1023;
+    unsigned char* stage0 = smem + w_region;
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * a.n_tile) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 4); }
+        mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+    const int spatial = a.tiles_x * a.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer ----------------------------------------------------------------------
+            if (a.resident) {                                   // n_tiles == 1 whenever the weights are resident
+                const int wbytes = iters * b_bytes;
+                mbar_expect_tx(&w_bar, wbytes);
+                for (int off = 0; off < wbytes; off += 16384)
+                    bulk_g2s(smem + off, a.w_packed + off, min(16384, wbytes - off), &w_bar);
+            }
+            int itg = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int nt = tile % a.n_tiles;
+                int t = tile / a.n_tiles;
+                const int tx = t % a.tiles_x; t /= a.tiles_x;
+                const int ty = t % a.tiles_y;
+                const int n_img = t / a.tiles_y;
+                const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+                const unsigned char* wsrc = a.w_packed + (size_t)nt * iters * b_bytes;
+                int it = 0;
+                for (int seg = 0; seg < a.nseg; ++seg) {
+                    const CUtensorMap* map = seg == 0 ? &map0 : &map1;
+                    for (int ch = 0; ch < a.chunks[seg]; ++ch) {
+                        for (int s = 0; s < a.ks; ++s, ++it, ++itg) {
+                            const int st = itg % a.stages;
+                            mbar_wait(empty_bar + st, ((itg / a.stages) & 1) ^ 1);
+                            unsigned char* sa = stage0 + (size_t)st * stage_bytes;
+                            mbar_expect_tx(full_bar + st, a_bytes + (a.resident ? 0 : b_bytes));
+                            tma_load_4d(sa, map, ch * CK, x0 + s - halo / 2, y0 - halo / 2, n_img, full_bar + st);
+                            if (!a.resident) bulk_g2s(sa + a_bytes, wsrc + (size_t)it * b_bytes, b_bytes, full_bar + st);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ------------------------------------------------------------------------
+            const uint32_t idesc = make_idesc(a.n_tile);
+            if (a.resident) mbar_wait(&w_bar, 0);
+            int itg = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tcount) {
+                const int buf = tcount & 1;
+                mbar_wait(acc_empty + buf, ((tcount >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_d + (uint32_t)(buf * a.n_tile);
+                for (int it = 0; it < iters; ++it, ++itg) {
+                    const int st = itg % a.stages;
+                    mbar_wait(full_bar + st, (itg / a.stages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(stage0 + (size_t)st * stage_bytes);
+                    const uint32_t sb = a.resident ? smem_u32(smem) + it * b_bytes : sa + a_bytes;
+                    for (int r = 0; r < a.ks; ++r) {
+#pragma unroll
+                        for (int kk = 0; kk < CK / 16; ++kk) {
+                            const uint64_t ad = make_desc<CK>(sa + r * (TILE_W * ROW_BYTES) + kk * 32);
+                            const uint64_t bd = make_desc<CK>(sb + r * (a.n_tile * ROW_BYTES) + kk * 32);
+                            umma_bf16(d, ad, bd, idesc, (it | r | kk) != 0);
+                        }
+                    }
+                    umma_commit(empty_bar + st);
+                }
+                umma_commit(acc_full + buf);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4 -------------------------------------------
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tcount) {
+            const int buf = tcount & 1;
+            const int nt = tile % a.n_tiles;
+            int t = tile / a.n_tiles;
+            const int tx = t % a.tiles_x; t /= a.tiles_x;
+            const int ty = t % a.tiles_y;
+            const int n_img = t / a.tiles_y;
+            const int y = ty * TILE_H + row / TILE_W, x = tx * TILE_W + row % TILE_W;
+            const bool valid = (y < a.H) && (x < a.W);
+            const int n0 = nt * a.n_tile;
+            mbar_wait(acc_full + buf, (tcount >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int j = 0; j < a.n_tile / 16; ++j) {
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + buf * a.n_tile + j * 16, v);
+                const int c0 = n0 + j * 16;
+                if (a.bias != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += (c0 + i < a.cout) ? __ldg(a.bias + c0 + i) : 0.f;
+                }
+                if (!valid) continue;
+                if (a.out_nchw_f32) {
+                    float* o = reinterpret_cast<float*>(a.out);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.cout) o[(((size_t)n_img * a.cout + c0 + i) * a.H + y) * a.W + x] = v[i];
+                } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + (((size_t)n_img * a.H + y) * a.W + x) * a.cout_stride + c0;
+                    if (c0 + 16 <= a.cout) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        uint4* o4 = reinterpret_cast<uint4*>(o);
+                        o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < a.cout) o[i] = __float2bfloat16_rn(v[i]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);        // 4 warps -> accumulator free for tile i+2
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -351,11 +528,8 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
     a.out_nchw_f32 = out_nchw_f32; a.bias = bias; a.w_packed = reinterpret_cast<const unsigned char*>(w_packed); a.out = out;
     const int row_bytes = pl.ck * 2;
     const int a_bytes = (TILE_H + ks - 1) * TILE_W * row_bytes, b_bytes = ks * pl.n_tile * row_bytes;
-    const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
-    int stages = pl.iters < MAX_STAGES ? pl.iters : MAX_STAGES;
-    while (stages > 1 && (size_t)stages * stage_bytes > 200 * 1024) --stages;
-    a.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024;            // + slack for the 1024-byte alignment
+    a.n_tiles = pl.n_tiles;
+    a.num_tiles = a.tiles_x * a.tiles_y * B * pl.n_tiles;
 
     CUtensorMap m0, m1;
     rc = encode_map(&m0, x1, B, H, W, c1_stride, pl.ck, TILE_H + ks - 1);
@@ -363,14 +537,48 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
     rc = encode_map(&m1, cin2 > 0 ? x2 : x1, B, H, W, cin2 > 0 ? c2_stride : c1_stride, pl.ck, TILE_H + ks - 1);
     if (rc != UAPS_OK) return rc;
 
-    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)pl.n_tiles, 1);
+    static const bool use_v1 = getenv("UAPS_CONV_V1") != nullptr;       // A/B knob for profiling, not part of the ABI
     cudaError_t e;
+    if (use_v1) {
+        const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
+        int stages = pl.iters < MAX_STAGES ? pl.iters : MAX_STAGES;
+        while (stages > 1 && (size_t)stages * stage_bytes > 200 * 1024) --stages;
+        a.stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + 1024;
+        dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)pl.n_tiles, 1);
 #define UAPS_CONV_LAUNCH(CKV)                                                                                   \
-    e = cudaFuncSetAttribute(conv_igemm_kernel<CKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return (int)e;                                                                        \
-    conv_igemm_kernel<CKV><<<grid, THREADS, smem, stream>>>(m0, m1, a);
-    if (pl.ck == 64) { UAPS_CONV_LAUNCH(64) } else if (pl.ck == 32) { UAPS_CONV_LAUNCH(32) } else { UAPS_CONV_LAUNCH(16) }
+        e = cudaFuncSetAttribute(conv_igemm_kernel<CKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e != cudaSuccess) return (int)e;                                                                        \
+        conv_igemm_kernel<CKV><<<grid, THREADS, smem, stream>>>(m0, m1, a);
+        if (pl.ck == 64) { UAPS_CONV_LAUNCH(64) } else if (pl.ck == 32) { UAPS_CONV_LAUNCH(32) } else { UAPS_CONV_LAUNCH(16) }
 #undef UAPS_CONV_LAUNCH
+    } else {
+        // persistent kernel: weights resident when they fit; as many stages as a budget of ~100 KB per CTA gives
+        const int wbytes = pl.iters * b_bytes;
+        a.resident = (pl.n_tiles == 1 && wbytes <= W_RESIDENT_MAX) ? 1 : 0;
+        const int w_region = a.resident ? ((wbytes + 1023) & ~1023) : 0;
+        const int stage_bytes = (a_bytes + (a.resident ? 0 : b_bytes) + 1023) & ~1023;
+        int stages = MAX_STAGES;
+        while (stages > 2 && (size_t)w_region + (size_t)stages * stage_bytes > 110 * 1024) --stages;
+        if ((size_t)w_region + (size_t)stages * stage_bytes > 220 * 1024) stages = 2;
+        while (stages > 1 && (size_t)w_region + (size_t)stages * stage_bytes > 220 * 1024) --stages;
+        a.stages = stages;
+        const size_t smem = (size_t)w_region + (size_t)stages * stage_bytes + 1024;
+        int tmem_cols = 32;
+        while (tmem_cols < 2 * pl.n_tile) tmem_cols <<= 1;
+        int per_sm = (int)((227 * 1024) / (smem + 2048));
+        if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        long long gridx = (long long)device_info().sm_count * per_sm;
+        if (gridx > a.num_tiles) gridx = a.num_tiles;
+#define UAPS_CONV_LAUNCH2(CKV)                                                                                             \
+        e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<CKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e != cudaSuccess) return (int)e;                                                                                   \
+        conv_igemm_persistent_kernel<CKV><<<(unsigned)gridx, THREADS2, smem, stream>>>(m0, m1, a);
+        if (pl.ck == 64) { UAPS_CONV_LAUNCH2(64) } else if (pl.ck == 32) { UAPS_CONV_LAUNCH2(32) } else { UAPS_CONV_LAUNCH2(16) }
+#undef UAPS_CONV_LAUNCH2
+    }
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
