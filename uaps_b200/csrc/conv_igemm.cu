@@ -50,6 +50,7 @@ struct ConvArgs {
     int num_tiles;       // spatial tiles x n_tiles (persistent kernel)
     int n_tiles;
     int resident;        // 1: this layer's packed weights stay in shared memory for the whole kernel
+    int xhalo;           // 1 (resident layers): ONE activation box with an x halo per chunk serves all 9 taps
     const float* bias;   // [>= n_tiles * n_tile] or null
     const unsigned char* w_packed;
     void* out;
@@ -64,6 +65,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     constexpr uint64_t span = CK * 2;                                    // 32 / 64 / 128 bytes
     constexpr uint64_t layout = (CK == 64) ? 2 : (CK == 32 ? 4 : 6);     // SWIZZLE_128B / 64B / 32B
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (((8 * span) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+// same, explicit stride between 8-row groups (x-halo tiles: an image row is TILE_W + 2 pixels apart)
+template <int CK>
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+    constexpr uint64_t layout = (CK == 64) ? 2 : (CK == 32 ? 4 : 6);
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, both K-major, N>>3, M>>4
 __device__ __forceinline__ uint32_t make_idesc(int n) {
@@ -222,10 +229,13 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = a.ks - 1;
-    const int a_bytes = (TILE_H + halo) * TILE_W * ROW_BYTES;
-    const int b_bytes = a.ks * a.n_tile * ROW_BYTES;
-    const int iters = (a.chunks[0] + (a.nseg > 1 ? a.chunks[1] : 0)) * a.ks;
-    const int w_region = a.resident ? ((iters * b_bytes + 1023) & ~1023) : 0;
+    const int box_w = a.xhalo ? TILE_W + halo : TILE_W;
+    const int a_bytes = (TILE_H + halo) * box_w * ROW_BYTES;
+    const int b_bytes = a.ks * a.n_tile * ROW_BYTES;                // the three r-blocks of one (chunk, s)
+    const int s_per_it = a.xhalo ? a.ks : 1;                          // horizontal taps served by one stage
+    const int iters = (a.chunks[0] + (a.nseg > 1 ? a.chunks[1] : 0)) * a.ks / s_per_it;
+    const int w_total = (a.chunks[0] + (a.nseg > 1 ? a.chunks[1] : 0)) * a.ks * b_bytes;
+    const int w_region = a.resident ? ((w_total + 1023) & ~1023) : 0;
     const int stage_bytes = (a_bytes + (a.resident ? 0 : b_bytes) + 1023) & ~1023;
     unsigned char* stage0 = smem + w_region;
 
@@ -249,7 +259,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
         if (lane == 0) {
             // ---- TMA producer ----------------------------------------------------------------------
             if (a.resident) {                                   // n_tiles == 1 whenever the weights are resident
-                const int wbytes = iters * b_bytes;
+                const int wbytes = w_total;
                 mbar_expect_tx(&w_bar, wbytes);
                 for (int off = 0; off < wbytes; off += 16384)
                     bulk_g2s(smem + off, a.w_packed + off, min(16384, wbytes - off), &w_bar);
@@ -262,17 +272,18 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
                 const int ty = t % a.tiles_y;
                 const int n_img = t / a.tiles_y;
                 const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-                const unsigned char* wsrc = a.w_packed + (size_t)nt * iters * b_bytes;
+                const unsigned char* wsrc = a.w_packed + (size_t)nt * w_total;
                 int it = 0;
                 for (int seg = 0; seg < a.nseg; ++seg) {
                     const CUtensorMap* map = seg == 0 ? &map0 : &map1;
                     for (int ch = 0; ch < a.chunks[seg]; ++ch) {
-                        for (int s = 0; s < a.ks; ++s, ++it, ++itg) {
+                        for (int s = 0; s < a.ks; s += s_per_it, ++it, ++itg) {
                             const int st = itg % a.stages;
                             mbar_wait(empty_bar + st, ((itg / a.stages) & 1) ^ 1);
                             unsigned char* sa = stage0 + (size_t)st * stage_bytes;
                             mbar_expect_tx(full_bar + st, a_bytes + (a.resident ? 0 : b_bytes));
-                            tma_load_4d(sa, map, ch * CK, x0 + s - halo / 2, y0 - halo / 2, n_img, full_bar + st);
+                            // xhalo: one box [18][10][CK] starting one pixel left of the tile; else one box per tap s
+                            tma_load_4d(sa, map, ch * CK, x0 + (a.xhalo ? 0 : s) - halo / 2, y0 - halo / 2, n_img, full_bar + st);
                             if (!a.resident) bulk_g2s(sa + a_bytes, wsrc + (size_t)it * b_bytes, b_bytes, full_bar + st);
                         }
                     }
@@ -296,13 +307,18 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
                     mbar_wait(full_bar + st, (itg / a.stages) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sa = smem_u32(stage0 + (size_t)st * stage_bytes);
-                    const uint32_t sb = a.resident ? smem_u32(smem) + it * b_bytes : sa + a_bytes;
-                    for (int r = 0; r < a.ks; ++r) {
+                    for (int s = 0; s < s_per_it; ++s) {
+                        // weights of (chunk, s): resident layers index the whole packed image, others their stage
+                        const uint32_t sb = a.resident ? smem_u32(smem) + (it * s_per_it + s) * b_bytes : sa + a_bytes;
+                        for (int r = 0; r < a.ks; ++r) {
 #pragma unroll
-                        for (int kk = 0; kk < CK / 16; ++kk) {
-                            const uint64_t ad = make_desc<CK>(sa + r * (TILE_W * ROW_BYTES) + kk * 32);
-                            const uint64_t bd = make_desc<CK>(sb + r * (a.n_tile * ROW_BYTES) + kk * 32);
-                            umma_bf16(d, ad, bd, idesc, (it | r | kk) != 0);
+                            for (int kk = 0; kk < CK / 16; ++kk) {
+                                // xhalo tile rows are (y, x) with x in [0, 10): tap (r, s) starts r rows down, s pixels right,
+                                // and consecutive 8-pixel groups are box_w pixels apart
+                                const uint64_t ad = make_desc_sbo<CK>(sa + (r * box_w + s) * ROW_BYTES + kk * 32, box_w * ROW_BYTES);
+                                const uint64_t bd = make_desc<CK>(sb + r * (a.n_tile * ROW_BYTES) + kk * 32);
+                                umma_bf16(d, ad, bd, idesc, (it | s | r | kk) != 0);
+                            }
                         }
                     }
                     umma_commit(empty_bar + st);
@@ -467,12 +483,12 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-int encode_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, int ck, int box_h) {
+int encode_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, int ck, int box_h, int box_w = TILE_W) {
     EncodeTiledFn encode = encode_tiled_fn();
     if (encode == nullptr) return UAPS_ENODEV;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)ck, (cuuint32_t)TILE_W, (cuuint32_t)box_h, 1};
+    cuuint32_t box[4] = {(cuuint32_t)ck, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapSwizzle sw = ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -531,13 +547,18 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
     a.n_tiles = pl.n_tiles;
     a.num_tiles = a.tiles_x * a.tiles_y * B * pl.n_tiles;
 
+    static const bool use_v1 = getenv("UAPS_CONV_V1") != nullptr;       // A/B knobs for profiling, not part of the ABI
+    static const bool no_xhalo = getenv("UAPS_CONV_NO_XHALO") != nullptr;
+    const int wbytes_all = pl.iters * b_bytes;
+    a.resident = (!use_v1 && pl.n_tiles == 1 && wbytes_all <= W_RESIDENT_MAX) ? 1 : 0;
+    a.xhalo = (a.resident && ks == 3 && !no_xhalo) ? 1 : 0;
+    const int box_w = a.xhalo ? TILE_W + 2 : TILE_W;
     CUtensorMap m0, m1;
-    rc = encode_map(&m0, x1, B, H, W, c1_stride, pl.ck, TILE_H + ks - 1);
+    rc = encode_map(&m0, x1, B, H, W, c1_stride, pl.ck, TILE_H + ks - 1, box_w);
     if (rc != UAPS_OK) return rc;
-    rc = encode_map(&m1, cin2 > 0 ? x2 : x1, B, H, W, cin2 > 0 ? c2_stride : c1_stride, pl.ck, TILE_H + ks - 1);
+    rc = encode_map(&m1, cin2 > 0 ? x2 : x1, B, H, W, cin2 > 0 ? c2_stride : c1_stride, pl.ck, TILE_H + ks - 1, box_w);
     if (rc != UAPS_OK) return rc;
 
-    static const bool use_v1 = getenv("UAPS_CONV_V1") != nullptr;       // A/B knob for profiling, not part of the ABI
     cudaError_t e;
     if (use_v1) {
         const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
@@ -554,10 +575,9 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
 #undef UAPS_CONV_LAUNCH
     } else {
         // persistent kernel: weights resident when they fit; as many stages as a budget of ~100 KB per CTA gives
-        const int wbytes = pl.iters * b_bytes;
-        a.resident = (pl.n_tiles == 1 && wbytes <= W_RESIDENT_MAX) ? 1 : 0;
-        const int w_region = a.resident ? ((wbytes + 1023) & ~1023) : 0;
-        const int stage_bytes = (a_bytes + (a.resident ? 0 : b_bytes) + 1023) & ~1023;
+        const int w_region = a.resident ? ((wbytes_all + 1023) & ~1023) : 0;
+        const int a_bytes2 = (TILE_H + ks - 1) * box_w * row_bytes;
+        const int stage_bytes = (a_bytes2 + (a.resident ? 0 : b_bytes) + 1023) & ~1023;
         int stages = MAX_STAGES;
         while (stages > 2 && (size_t)w_region + (size_t)stages * stage_bytes > 110 * 1024) --stages;
         if ((size_t)w_region + (size_t)stages * stage_bytes > 220 * 1024) stages = 2;
