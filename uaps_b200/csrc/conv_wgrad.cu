@@ -4,10 +4,13 @@
 // GEMM per tap: M = output channels, N = a 16/32-wide chunk of input channels, K = pixels.  Both
 // operands are channels-last, so the reduction dimension (pixels) is the OUTER one: they are fed to the
 // tensor core as MN-major operands straight from the TMA boxes, no transpose pass:
-//   A = dY tile  [128 px][64 ch] x 2 boxes (SWIZZLE_128B): M-major, 8 pixel rows per swizzle atom;
-//       channels beyond Cout are zero (TMA out-of-bounds fill / a zeroed second box).
-//   B = X halo tile [(16+2)*8 px][n_chunk ch] per horizontal tap s (SWIZZLE_64B / 32B): N-major; the three
-//       vertical taps r are the same tile read 8 pixel rows (= one atom) further down, as in the forward kernel.
+//   A = dY tile  [128 px][min(Cout,64) ch] (x 2 boxes when Cout > 64): M-major, 8 pixel rows per swizzle atom.
+//       The instruction is always M = 128; when the layer has fewer output channels the remaining M groups are
+//       pointed (LBO) at other rows of the same tile -- their accumulator lanes hold finite garbage and are never
+//       read.  (A 64-channel box on a 16-channel tensor would be zero-filled by TMA, but out-of-bounds boxes are
+//       served one pixel at a time: measured 13x slower.)
+//   B = ONE X halo tile [(16+2) x (8+2) px][n_chunk ch] per pixel tile: N-major; tap (r, s) is the same tile read
+//       from row r, pixel s, with 8-pixel K atoms one image row (10 pixels) apart (SBO), as in the forward kernel.
 // The 9 tap accumulators (9 x n_chunk fp32 columns) stay in TMEM across all pixel tiles of the CTA
 // (split-K over CTAs), then are added to dW with fp32 reductions.
 #include "tc_common.cuh"
@@ -19,24 +22,24 @@ using namespace uaps::tc;
 constexpr int TILE_H = 16, TILE_W = 8, TILE_M = 128;
 constexpr int THREADS = 128;
 constexpr int STAGES = 3;
-constexpr int A_BOX_BYTES = 128 * 128;            // 128 pixels x 64 channels x 2 B
 
 struct WgradArgs {
     int B, H, W;
     int cout, cin_total, ci_offset;
     int ks, n_chunk;
     int tiles_x, tiles_y, tiles_total, tiles_per_cta;
+    int a_ch;                                      // channels per dY box: 16 / 32 / 64
     int two_boxes;                                 // cout > 64: second 64-channel box carries data
     float* dw;
 };
 
 // MN-major descriptors (cute::UMMA canonical forms, units of 16 bytes):
 //   SW128: ((8,n),(8,k)):((1,LBO),(8,SBO))   SW64: ((4,n),(8,k)):((1,LBO),(4,SBO))   SW32: ((2,n),(8,k)):((1,LBO),(2,SBO))
-// k rows are `span` bytes apart, 8 of them form an atom, SBO = 8 * span; LBO = distance between MN groups.
-__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t span, uint32_t lbo_bytes) {
+// k rows are `span` bytes apart, 8 of them form an atom; SBO = distance between K atoms, LBO = between MN groups.
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t span, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     const uint64_t layout = span == 128 ? 2 : (span == 64 ? 4 : 6);
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)(((8 * span) >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
 // D = F32, A = B = BF16, both MN-major (bits 15, 16), N >> 3, M >> 4
 __device__ __forceinline__ uint32_t idesc_mn(int n) {
@@ -52,11 +55,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = a.ks - 1;
+    const int box_w = TILE_W + halo;
+    const int row_a = a.a_ch * 2;                                     // 32 / 64 / 128 bytes per pixel row of A
     const int row_b = a.n_chunk * 2;                                  // 32 or 64 bytes per pixel row of B
-    const int b_box = (TILE_H + halo) * TILE_W * row_b;
-    const int a_bytes = 2 * A_BOX_BYTES;
-    const int stage_bytes = (a_bytes + a.ks * b_box + 1023) & ~1023;
+    const int a_box = TILE_M * row_a;
+    const int a_bytes = (a.two_boxes ? 2 : 1) * a_box;
+    const int b_bytes = (TILE_H + halo) * box_w * row_b;
+    const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
     const int ntaps = a.ks * a.ks;
+    // stride between the 128 / a_ch M groups: the second real box, or (fewer channels than M) one atom of the
+    // same tile -- in bounds, finite, and its accumulator lanes are ignored
+    const uint32_t lbo_a = a.two_boxes ? (uint32_t)a_box : (uint32_t)(8 * row_a);
 
     const int split = blockIdx.x, nc = blockIdx.y, mt = blockIdx.z;
     const int tile_lo = split * a.tiles_per_cta;
@@ -70,13 +79,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
         mbar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (!a.two_boxes) {                               // channels 64..127 of the M operand are zero for the whole kernel
-        for (int s = 0; s < STAGES; ++s) {
-            uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes + A_BOX_BYTES);
-            for (int i = threadIdx.x; i < A_BOX_BYTES / 16; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -95,34 +97,37 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
                     const int st = it % STAGES;
                     mbar_wait(empty_bar + st, ((it / STAGES) & 1) ^ 1);
                     unsigned char* sa = smem + (size_t)st * stage_bytes;
-                    mbar_expect_tx(full_bar + st, (a.two_boxes ? 2 : 1) * A_BOX_BYTES + a.ks * b_box);
+                    mbar_expect_tx(full_bar + st, a_bytes + b_bytes);
                     tma_load_4d(sa, &map_dy, mt * 128, x0, y0, n_img, full_bar + st);
-                    if (a.two_boxes) tma_load_4d(sa + A_BOX_BYTES, &map_dy, mt * 128 + 64, x0, y0, n_img, full_bar + st);
-                    for (int s = 0; s < a.ks; ++s)
-                        tma_load_4d(sa + a_bytes + s * b_box, &map_x, nc * a.n_chunk, x0 + s - halo / 2, y0 - halo / 2, n_img,
-                                    full_bar + st);
+                    if (a.two_boxes) tma_load_4d(sa + a_box, &map_dy, mt * 128 + 64, x0, y0, n_img, full_bar + st);
+                    tma_load_4d(sa + a_bytes, &map_x, nc * a.n_chunk, x0 - halo / 2, y0 - halo / 2, n_img, full_bar + st);
                 }
             }
             __syncwarp();
         } else if (warp == 1) {
             if (lane == 0) {
-                const uint32_t idesc = idesc_mn(a.n_chunk);
+                // The three horizontal taps of a row r are ONE instruction: the N-major B descriptor's group
+                // stride (LBO) is one pixel, so N group s is the same tile shifted by s pixels (N = 3 * n_chunk,
+                // accumulator columns [s][ci]).  24 MMAs per pixel tile instead of 72 -- the issuing thread, not
+                // the tensor pipe, was the limit.  Descriptors advance by adding to the 14-bit start field.
+                const uint32_t idesc = idesc_mn(a.ks * a.n_chunk);
                 for (int it = 0; it < ntiles; ++it) {
                     const int st = it % STAGES;
                     mbar_wait(full_bar + st, (it / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
-                    for (int r = 0; r < a.ks; ++r)
-                        for (int s = 0; s < a.ks; ++s) {
-                            const uint32_t d = tmem_d + (uint32_t)((r * a.ks + s) * a.n_chunk);
+                    const uint64_t ad0 = desc_mn(sa, row_a, lbo_a, 8 * row_a);
+                    const uint64_t bd0 = desc_mn(sb, row_b, row_b, box_w * row_b);
+                    for (int r = 0; r < a.ks; ++r) {
+                        const uint32_t d = tmem_d + (uint32_t)(r * a.ks * a.n_chunk);
 #pragma unroll
-                            for (int kk = 0; kk < TILE_M / 16; ++kk) {            // 16 pixels per MMA
-                                const uint64_t ad = desc_mn(sa + kk * 16 * 128, 128, A_BOX_BYTES);
-                                const uint64_t bd = desc_mn(sb + s * b_box + (r * TILE_W + kk * 16) * row_b, row_b, 0);
-                                umma_bf16(d, ad, bd, idesc, (it | kk) != 0);
-                            }
+                        for (int kk = 0; kk < TILE_M / 16; ++kk) {                // 16 pixels (two image rows of the tile) per MMA
+                            const uint64_t ad = ad0 + (uint64_t)((kk * 16 * row_a) >> 4);
+                            const uint64_t bd = bd0 + (uint64_t)((((r + 2 * kk) * box_w) * row_b) >> 4);
+                            umma_bf16(d, ad, bd, idesc, (it | kk) != 0);
                         }
+                    }
                     umma_commit(empty_bar + st);
                 }
                 umma_commit(&done_bar);
@@ -172,12 +177,12 @@ EncodeTiledFn encode_fn() {
     }();
     return fn;
 }
-int encode(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cs, int box_c, int box_h) {
+int encode(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cs, int box_c, int box_h, int box_w) {
     EncodeTiledFn f = encode_fn();
     if (f == nullptr) return UAPS_ENODEV;
     cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TILE_W, (cuuint32_t)box_h, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     return f(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -202,21 +207,44 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     a.tiles_x = (W + TILE_W - 1) / TILE_W; a.tiles_y = (H + TILE_H - 1) / TILE_H;
     a.tiles_total = a.tiles_x * a.tiles_y * B;
     a.two_boxes = cout > 64;
+    const int cout_pad = (cout + 15) / 16 * 16;
+    a.a_ch = cout_pad >= 64 ? 64 : (cout_pad % 32 == 0 ? 32 : 16);
+    if (dy_c_stride < a.a_ch) return UAPS_ERANGE;                            // the dY box must lie inside the tensor's channels
     a.dw = dw;
+    if (cin_pad != cin) return UAPS_ERANGE;                                  // callers pad Cin=3 layers on their side (see conv.py)
     const int n_chunks = cin_pad / a.n_chunk, m_tiles = (cout + 127) / 128;
-    int splits = (2 * device_info().sm_count + n_chunks * m_tiles - 1) / (n_chunks * m_tiles);
-    if (splits > a.tiles_total) splits = a.tiles_total;
-    if (splits < 1) splits = 1;
+    const int row_a = a.a_ch * 2, row_b = a.n_chunk * 2;
+    const int a_bytes = (a.two_boxes ? 2 : 1) * TILE_M * row_a, b_bytes = (TILE_H + ks - 1) * (TILE_W + ks - 1) * row_b;
+    const size_t smem = (size_t)STAGES * ((a_bytes + b_bytes + 1023) & ~1023) + 1024;
+    // split-K: enough CTAs to fill the machine (as many as fit per SM by shared memory and the 512 TMEM columns),
+    // but at least 4 pixel tiles per CTA so the 9 * n_chunk * Cout reductions of the epilogue stay amortised
+    int tmem_cols = 32;
+    while (tmem_cols < ks * ks * a.n_chunk) tmem_cols <<= 1;
+    int per_sm = (int)((227 * 1024) / (smem + 2048));
+    if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    // split-K factor: trade main-loop length against the fp32 reductions of the epilogue (every split adds
+    // cout * cin * taps of them; measured ~125 reductions/ns chip-wide) -- evaluate a simple cost model
+    const int slots = per_sm * device_info().sm_count;
+    const int groups = n_chunks * m_tiles;
+    const double tile_us = 1500.0 / 1900.0;                                  // ~1500 cycles per pixel tile (MMA issue bound)
+    const double red_per_split_us = (double)cout * cin * ks * ks / 125e3;
+    int best = 1;
+    double best_t = 1e30;
+    for (int sp = 1; sp <= a.tiles_total && sp * groups <= 4 * slots; sp = sp < 8 ? sp + 1 : sp + sp / 4) {
+        const int per_cta = (a.tiles_total + sp - 1) / sp;
+        const int waves = (sp * groups + slots - 1) / slots;
+        const double t = waves * per_cta * tile_us + sp * red_per_split_us + 3.0;
+        if (t < best_t) { best_t = t; best = sp; }
+    }
+    int splits = best;
     a.tiles_per_cta = (a.tiles_total + splits - 1) / splits;
     splits = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    // the epilogue writes only real input channels: a padded chunk's extra columns (ci >= cin) must be skipped
-    if (cin_pad != cin) return UAPS_ERANGE;                                  // callers pad Cin=3 layers on their side (see conv.py)
-    const int row_b = a.n_chunk * 2, b_box = (TILE_H + ks - 1) * TILE_W * row_b;
-    const size_t smem = (size_t)STAGES * ((2 * A_BOX_BYTES + ks * b_box + 1023) & ~1023) + 1024;
     CUtensorMap mdy, mx;
-    int rc = encode(&mdy, dy, B, H, W, dy_c_stride, 64, TILE_H);
+    int rc = encode(&mdy, dy, B, H, W, dy_c_stride, a.a_ch, TILE_H, TILE_W);
     if (rc != UAPS_OK) return rc;
-    rc = encode(&mx, x, B, H, W, x_c_stride, a.n_chunk, TILE_H + ks - 1);
+    rc = encode(&mx, x, B, H, W, x_c_stride, a.n_chunk, TILE_H + ks - 1, TILE_W + ks - 1);
     if (rc != UAPS_OK) return rc;
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
