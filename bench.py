@@ -42,7 +42,8 @@ K, C, B, H, W = 4, 4, 64, 256, 256
 CW1 = CW2 = 0.1
 WORKLOAD = f"fused_loss_fwd_bwd K={K} C={C} B={B}/gpu {H}x{W} fp32-logits"
 CPU_SAMPLE_B = 8                       # bounded CPU sample: 8 x 256 x 256 pixels per step
-TRAIN_B = 16                           # labeled + unlabeled images per GPU for the secondary train-step line
+TRAIN_B = 64                           # labeled + unlabeled images per GPU (BASELINE configs[2]: batch 64+64)
+TRAIN_B_FP32 = 16                      # the fp32 cuDNN comparison path runs a quarter batch (it is ~3x slower)
 
 
 def measured_hbm_peak():
@@ -285,7 +286,7 @@ def run_ours(args):
     if not args.no_train_step:
         try:
             train = train_step_bench(dev, group, world, rank, compute="bf16")
-            train["fp32_path"] = train_step_bench(dev, group, world, rank, compute="fp32")
+            train["fp32_path"] = train_step_bench(dev, group, world, rank, compute="fp32", batch=TRAIN_B_FP32)
         except Exception as e:
             train = {"error": repr(e)[:300]}
 
@@ -366,8 +367,8 @@ def loss_sweep(dev, lib, L, iters: int = 10):
     return out
 
 
-def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3, compute: str = "bf16"):
-    """Secondary: full UAPS iteration at the NEU shape (3x256x256, C=4, K=4), TRAIN_B + TRAIN_B images per GPU."""
+def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3, compute: str = "bf16", batch: int = TRAIN_B):
+    """Secondary: full UAPS iteration at the NEU shape (3x256x256, C=4, K=4), batch + batch images per GPU."""
     import torch.distributed as dist
     from uaps_b200.train import UAPSTrainer
     from uaps_b200.unet import UNet_UAPS
@@ -375,9 +376,9 @@ def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3, c
     model = UNet_UAPS(3, C, compute=compute).to(dev)
     trainer = UAPSTrainer(model, group=group)
     gen = torch.Generator().manual_seed(1337 + rank)
-    xl_h = torch.randn(TRAIN_B, 3, H, W, generator=gen).pin_memory()
-    xu_h = torch.randn(TRAIN_B, 3, H, W, generator=gen).pin_memory()
-    yl_h = torch.randint(0, C, (TRAIN_B, H, W), generator=gen).pin_memory()
+    xl_h = torch.randn(batch, 3, H, W, generator=gen).pin_memory()
+    xu_h = torch.randn(batch, 3, H, W, generator=gen).pin_memory()
+    yl_h = torch.randint(0, C, (batch, H, W), generator=gen).pin_memory()
     loss_h = torch.empty((), dtype=torch.float32).pin_memory()
 
     def it():
@@ -402,8 +403,8 @@ def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3, c
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item() / steps
-    return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "images_per_s": 2 * TRAIN_B * world * 1e3 / ms, "unit": "iters/s",
-            "loss": float(loss_h), "config": f"UNet_UAPS 3x{H}x{W} C={C} K={K}, {TRAIN_B}+{TRAIN_B} images/GPU, "
+    return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "images_per_s": 2 * batch * world * 1e3 / ms, "unit": "iters/s",
+            "loss": float(loss_h), "config": f"UNet_UAPS 3x{H}x{W} C={C} K={K}, {batch}+{batch} images/GPU, "
             f"dp{world}, host images in the timed region (e2e)",
             "convs": "tcgen05 implicit GEMM (fprop + dgrad), bf16 channels-last; wgrad/BN/pool/upsample via torch"
             if compute == "bf16" else "cuDNN fp32 (reference-precision path)"}

@@ -213,9 +213,12 @@ size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks);
  * swapped: pass cout = W's Cin, cin1 = W's Cout). */
 int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks,
                            int transpose, cudaStream_t stream);
+/* out2 (nullable): second bf16 NHWC output; output channels >= split (a multiple of 16) are written there
+ * at channel (c - split) -- the data gradient of a concat convolution lands in its two consumers' tensors. */
 int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
                     const float* bias, void* out, int out_c_stride, int out_nchw_f32,
-                    int B, int H, int W, int cin1, int cin2, int cout, int ks, cudaStream_t stream);
+                    int B, int H, int W, int cin1, int cin2, int cout, int ks,
+                    void* out2, int out2_c_stride, int split, cudaStream_t stream);
 
 /* Weight gradient on tcgen05 (MN-major operands straight from the channels-last tensors):
  * dw[co][ci_offset + ci][r][s] += sum_pixels dy[p][co] * x[p + (r-1, s-1)][ci].  dw is fp32 in torch layout

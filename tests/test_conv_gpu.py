@@ -124,3 +124,18 @@ def test_weight_gradient_of_concat_input():
         F.conv2d(torch.cat([skip, up], 1).bfloat16().float(), w, padding=1).backward(dy.bfloat16().float())
         dw = conv_wgrad(to_nhwc_bf16(dy), [to_nhwc_bf16(skip), to_nhwc_bf16(up)], c, 2 * c, 3)
         assert (dw - w.grad).abs().max().item() <= 2e-3 * w.grad.abs().max().item(), c
+
+
+def test_split_outputs_of_concat_data_gradient():
+    """The data gradient of a concat conv is written straight into two tensors (channels [0,c) and [c,2c))."""
+    from uaps_b200.conv import PackedConv, from_nhwc, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    for c in (16, 64):
+        w = (torch.randn(c, 2 * c, 3, 3, generator=g) * 0.05).to(dev)
+        dy = torch.randn(2, c, 32, 32, generator=g).to(dev)
+        conv = PackedConv(w, None, transpose=True)
+        whole = conv(to_nhwc_bf16(dy))
+        a, b = conv(to_nhwc_bf16(dy), split=c)
+        assert a.shape[-1] == c and b.shape[-1] == c
+        assert torch.equal(a, whole[..., :c]) and torch.equal(b, whole[..., c:])

@@ -54,7 +54,9 @@ class PackedConv:
                                                    ks, int(transpose), L.stream_ptr()), "uaps_conv_pack_weights")
         self.bias = None if bias is None else bias.detach().float().contiguous()
 
-    def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, out_nchw_f32: bool = False) -> torch.Tensor:
+    def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, out_nchw_f32: bool = False,
+                 split: int = 0):
+        """split > 0: return two NHWC tensors holding output channels [0, split) and [split, cout)."""
         L.require_cuda(x1)
         assert x1.dtype == torch.bfloat16 and x1.is_contiguous() and x1.dim() == 4
         B, H, W, c1s = x1.shape
@@ -66,15 +68,17 @@ class PackedConv:
             out = torch.empty((B, self.cout, H, W), dtype=torch.float32, device=x1.device)
             ocs = 0
         else:
-            ocs = pad16(self.cout)
-            alloc = torch.zeros if ocs != self.cout else torch.empty
+            ocs = pad16(self.cout) if not split else split
+            alloc = torch.zeros if (ocs != self.cout and not split) else torch.empty
             out = alloc((B, H, W, ocs), dtype=torch.bfloat16, device=x1.device)
+        out2 = torch.empty((B, H, W, self.cout - split), dtype=torch.bfloat16, device=x1.device) if split else None
         with torch.cuda.device(x1.device):
             L.check(L.lib().uaps_conv_fprop(x1.data_ptr(), c1s, None if x2 is None else x2.data_ptr(), c2s,
                                             self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(),
                                             out.data_ptr(), ocs, int(out_nchw_f32), B, H, W, self.cin1, self.cin2,
-                                            self.cout, self.ks, L.stream_ptr()), "uaps_conv_fprop")
-        return out
+                                            self.cout, self.ks, None if out2 is None else out2.data_ptr(),
+                                            0 if out2 is None else self.cout - split, split, L.stream_ptr()), "uaps_conv_fprop")
+        return out if not split else (out, out2)
 
 
 def conv_wgrad(dy_nhwc: torch.Tensor, xs, cout: int, cin_total: int, ks: int) -> torch.Tensor:
@@ -167,10 +171,15 @@ class _ConvFn(torch.autograd.Function):
             pad[..., :co] = gy_nhwc
             gy_nhwc = pad
         # data gradient: tcgen05 kernel, W'[ci][co] rotated by 180 degrees
-        gx = packed(weight, None, transpose=True)(gy_nhwc)              # [B,H,W,pad16(ci)]
         c1 = x1.shape[1]
-        g1 = _as_cl(gx[..., :c1]) if ctx.needs_input_grad[0] else None
-        g2 = _as_cl(gx[..., c1:ci]) if (x2 is not None and ctx.needs_input_grad[1]) else None
+        if x2 is None:
+            gx = packed(weight, None, transpose=True)(gy_nhwc)          # [B,H,W,pad16(ci)]
+            g1 = _as_cl(gx[..., :c1]) if ctx.needs_input_grad[0] else None
+            g2 = None
+        else:                                                            # concat conv: each consumer gets its own tensor
+            ga, gb2 = packed(weight, None, transpose=True)(gy_nhwc, split=c1)
+            g1 = _as_cl(ga) if ctx.needs_input_grad[0] else None
+            g2 = _as_cl(gb2) if ctx.needs_input_grad[1] else None
         # weight gradient: tcgen05 kernel on the same channels-last tensors (MN-major operands, no transposes)
         xs = [_nhwc_view(x1)] + ([] if x2 is None else [_nhwc_view(x2)])
         cin_pad = sum(t.shape[3] for t in xs)                 # the 3-channel network input is stored 16-padded

@@ -54,6 +54,8 @@ struct ConvArgs {
     const float* bias;   // [>= n_tiles * n_tile] or null
     const unsigned char* w_packed;
     void* out;
+    void* out2;          // optional second NHWC output: channels >= split go there (data gradient of a concat conv)
+    int split, out2_stride;
 };
 
 using namespace uaps::tc;
@@ -359,7 +361,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
                     for (int i = 0; i < 16; ++i)
                         if (c0 + i < a.cout) o[(((size_t)n_img * a.cout + c0 + i) * a.H + y) * a.W + x] = v[i];
                 } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + (((size_t)n_img * a.H + y) * a.W + x) * a.cout_stride + c0;
+                    const size_t pix = ((size_t)n_img * a.H + y) * a.W + x;
+                    __nv_bfloat16* o = (a.out2 != nullptr && c0 >= a.split)
+                        ? reinterpret_cast<__nv_bfloat16*>(a.out2) + pix * a.out2_stride + (c0 - a.split)
+                        : reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.cout_stride + c0;
                     if (c0 + 16 <= a.cout) {
                         uint32_t pk[8];
 #pragma unroll
@@ -525,7 +530,8 @@ UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, in
 
 UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
                              const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
-                             int cin1, int cin2, int cout, int ks, cudaStream_t stream) {
+                             int cin1, int cin2, int cout, int ks, void* out2, int out2_c_stride, int split,
+                             cudaStream_t stream) {
     Plan pl;
     int rc = make_plan(cout, cin1, cin2, ks, &pl);
     if (rc != UAPS_OK) return rc;
@@ -535,13 +541,18 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
     if (c1_stride < pl.seg_pad[0] || (c1_stride % 8) != 0 || (cin2 > 0 && (c2_stride < pl.seg_pad[1] || (c2_stride % 8) != 0)))
         return UAPS_ERANGE;
     if (!aligned_to(x1, 16) || (x2 && !aligned_to(x2, 16)) || !aligned_to(out, 16) || !aligned_to(w_packed, 16)) return UAPS_EALIGN;
-    if (!out_nchw_f32 && (out_c_stride < cout || (out_c_stride % 8) != 0)) return UAPS_ERANGE;
+    if (!out_nchw_f32 && (out_c_stride < (out2 != nullptr ? split : cout) || (out_c_stride % 8) != 0)) return UAPS_ERANGE;
+    if (out2 != nullptr && out2_c_stride < cout - split) return UAPS_ERANGE;
 
     ConvArgs a{};
     a.B = B; a.H = H; a.W = W; a.cout = cout; a.cout_stride = out_c_stride; a.n_tile = pl.n_tile; a.nseg = pl.nseg;
     a.chunks[0] = pl.chunks[0]; a.chunks[1] = pl.chunks[1]; a.ks = ks;
     a.tiles_x = (W + TILE_W - 1) / TILE_W; a.tiles_y = (H + TILE_H - 1) / TILE_H;
     a.out_nchw_f32 = out_nchw_f32; a.bias = bias; a.w_packed = reinterpret_cast<const unsigned char*>(w_packed); a.out = out;
+    a.out2 = out2; a.split = split; a.out2_stride = out2_c_stride;
+    if (out2 != nullptr && (out_nchw_f32 || (split % 16) != 0 || split <= 0 || split >= cout || (out2_c_stride % 8) != 0 ||
+                            !aligned_to(out2, 16) || getenv("UAPS_CONV_V1") != nullptr))
+        return UAPS_EINVAL;
     const int row_bytes = pl.ck * 2;
     const int a_bytes = (TILE_H + ks - 1) * TILE_W * row_bytes, b_bytes = ks * pl.n_tile * row_bytes;
     a.n_tiles = pl.n_tiles;
