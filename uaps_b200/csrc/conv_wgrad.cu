@@ -1,18 +1,18 @@
 // Weight gradient of the 3x3 / 1x1 convolutions on tcgen05 (UAPS_train.py:287 `loss.backward()` through
 // the nn.Conv2d layers of utilities/UAPS_unet.py:36,41,73,138):
 //     dW[co][ci][r][s] = sum over pixels p of dY[p][co] * X[p + (r-1, s-1)][ci]
-// GEMM per tap: M = output channels, N = a 16/32-wide chunk of input channels, K = pixels.  Both
-// operands are channels-last, so the reduction dimension (pixels) is the OUTER one: they are fed to the
+// GEMM per vertical tap r:  D_r[(s, ci)][co] = sum_pixels X[p + (r-1, s-1)][ci] * dY[p][co]
+//   M = (horizontal tap s) x (16/32-wide chunk of input channels), N = output channels, K = pixels.
+// Both operands are channels-last, so the reduction dimension (pixels) is the OUTER one: they are fed to the
 // tensor core as MN-major operands straight from the TMA boxes, no transpose pass:
-//   A = dY tile  [128 px][min(Cout,64) ch] (x 2 boxes when Cout > 64): M-major, 8 pixel rows per swizzle atom.
-//       The instruction is always M = 128; when the layer has fewer output channels the remaining M groups are
-//       pointed (LBO) at other rows of the same tile -- their accumulator lanes hold finite garbage and are never
-//       read.  (A 64-channel box on a 16-channel tensor would be zero-filled by TMA, but out-of-bounds boxes are
-//       served one pixel at a time: measured 13x slower.)
-//   B = ONE X halo tile [(16+2) x (8+2) px][n_chunk ch] per pixel tile: N-major; tap (r, s) is the same tile read
-//       from row r, pixel s, with 8-pixel K atoms one image row (10 pixels) apart (SBO), as in the forward kernel.
-// The 9 tap accumulators (9 x n_chunk fp32 columns) stay in TMEM across all pixel tiles of the CTA
-// (split-K over CTAs), then are added to dW with fp32 reductions.
+//   A = ONE X halo tile [(16+2) x (8+2) px][n_chunk ch]: M-major.  Its M-group stride (LBO) is ONE PIXEL, so M group
+//       s is the same tile shifted by s pixels -- the three horizontal taps ride in the M dimension, which costs
+//       nothing (an M=128 instruction takes N/2 cycles whatever M holds; groups beyond 3 alias further shifts and
+//       their accumulator lanes are never read).  8-pixel K atoms are one image row (10 pixels) apart (SBO).
+//   B = dY tile [128 px][min(Cout,64) ch] (x 2 boxes for Cout > 64): N-major, N = Cout of this CTA (<= 128).
+// Putting Cout on N and the taps on M makes the tensor time 12 * Cout cycles per 128-pixel tile (192 for the
+// 16-channel layers) instead of 576+ with the roles swapped.  The 3 accumulators D_r (3 x Cout fp32 columns) stay
+// in TMEM across all pixel tiles of the CTA (split-K over CTAs), then are added to dW with fp32 reductions.
 #include "tc_common.cuh"
 
 namespace uaps {
@@ -29,6 +29,7 @@ struct WgradArgs {
     int ks, n_chunk;
     int tiles_x, tiles_y, tiles_total, tiles_per_cta;
     int a_ch;                                      // channels per dY box: 16 / 32 / 64
+    int n_co;                                      // output channels per CTA (MMA N): multiple of 16, <= 128
     int two_boxes;                                 // cout > 64: second 64-channel box carries data
     float* dw;
 };
@@ -65,7 +66,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     const int ntaps = a.ks * a.ks;
     // stride between the 128 / a_ch M groups: the second real box, or (fewer channels than M) one atom of the
     // same tile -- in bounds, finite, and its accumulator lanes are ignored
-    const uint32_t lbo_a = a.two_boxes ? (uint32_t)a_box : (uint32_t)(8 * row_a);
+    const uint32_t lbo_dy = a.two_boxes ? (uint32_t)a_box : (uint32_t)(8 * row_a);   // N groups of dY (unused when one group)
+    const int n_co = a.n_co;                                          // output channels of this CTA (N of the MMA)
 
     const int split = blockIdx.x, nc = blockIdx.y, mt = blockIdx.z;
     const int tile_lo = split * a.tiles_per_cta;
@@ -73,11 +75,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     const int ntiles = tile_hi - tile_lo;
 
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < ntaps * a.n_chunk) tmem_cols <<= 1;
+    while ((int)tmem_cols < a.ks * n_co) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        mbar_init(&done_bar, 1);
+        // the ks vertical taps are issued by ks different warps (warps 1..ks): each commits once per stage / at the end
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, a.ks); }
+        mbar_init(&done_bar, a.ks);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -104,29 +107,29 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
                 }
             }
             __syncwarp();
-        } else if (warp == 1) {
+        } else if (warp <= a.ks) {
             if (lane == 0) {
                 // The three horizontal taps of a row r are ONE instruction: the N-major B descriptor's group
                 // stride (LBO) is one pixel, so N group s is the same tile shifted by s pixels (N = 3 * n_chunk,
-                // accumulator columns [s][ci]).  24 MMAs per pixel tile instead of 72 -- the issuing thread, not
-                // the tensor pipe, was the limit.  Descriptors advance by adding to the 14-bit start field.
-                const uint32_t idesc = idesc_mn(a.ks * a.n_chunk);
+                // accumulator columns [s][ci]).  And the three vertical taps r are issued by three different
+                // warps, each into its own accumulator: a single issuing thread, not the tensor pipe, was the
+                // limit (72 -> 24 -> 8 MMAs per issuing thread per pixel tile).
+                const int r = warp - 1;
+                const uint32_t idesc = idesc_mn(n_co);
+                const uint32_t d = tmem_d + (uint32_t)(r * n_co);
                 for (int it = 0; it < ntiles; ++it) {
                     const int st = it % STAGES;
                     mbar_wait(full_bar + st, (it / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
-                    const uint64_t ad0 = desc_mn(sa, row_a, lbo_a, 8 * row_a);
-                    const uint64_t bd0 = desc_mn(sb, row_b, row_b, box_w * row_b);
-                    for (int r = 0; r < a.ks; ++r) {
-                        const uint32_t d = tmem_d + (uint32_t)(r * a.ks * a.n_chunk);
+                    const uint32_t sdy = smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint32_t sx = sdy + a_bytes;
+                    const uint64_t xd0 = desc_mn(sx, row_b, row_b, box_w * row_b);        // A: X, M groups one pixel apart
+                    const uint64_t yd0 = desc_mn(sdy, row_a, lbo_dy, 8 * row_a);          // B: dY
 #pragma unroll
-                        for (int kk = 0; kk < TILE_M / 16; ++kk) {                // 16 pixels (two image rows of the tile) per MMA
-                            const uint64_t ad = ad0 + (uint64_t)((kk * 16 * row_a) >> 4);
-                            const uint64_t bd = bd0 + (uint64_t)((((r + 2 * kk) * box_w) * row_b) >> 4);
-                            umma_bf16(d, ad, bd, idesc, (it | kk) != 0);
-                        }
+                    for (int kk = 0; kk < TILE_M / 16; ++kk) {                    // 16 pixels (two image rows of the tile) per MMA
+                        const uint64_t xd = xd0 + (uint64_t)((((r + 2 * kk) * box_w) * row_b) >> 4);
+                        const uint64_t yd = yd0 + (uint64_t)((kk * 16 * row_a) >> 4);
+                        umma_bf16(d, xd, yd, idesc, (it | kk) != 0);
                     }
                     umma_commit(empty_bar + st);
                 }
@@ -134,19 +137,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
             }
             __syncwarp();
         }
-        // ---- epilogue: lane = output channel; 9 taps x n_chunk input channels -> fp32 reductions into dW
+        // ---- epilogue: lane = (horizontal tap s, input channel ci); columns = output channels -> fp32 reductions into dW
         mbar_wait(&done_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int co = mt * 128 + warp * 32 + lane;
-        for (int tap = 0; tap < ntaps; ++tap) {
-            for (int j = 0; j < a.n_chunk / 16; ++j) {
+        const int row = warp * 32 + lane;
+        const int s_tap = row / a.n_chunk, ci = a.ci_offset + nc * a.n_chunk + row % a.n_chunk;
+        const bool lane_ok = row < a.ks * a.n_chunk;
+        for (int r = 0; r < a.ks; ++r) {
+            for (int j = 0; j < n_co / 16; ++j) {
                 float v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + tap * a.n_chunk + j * 16, v);
-                if (co < a.cout) {
-                    const int ci0 = a.ci_offset + nc * a.n_chunk + j * 16;
+                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + r * n_co + j * 16, v);
+                if (lane_ok) {
+                    const int co0 = mt * 128 + j * 16;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        atomicAdd(a.dw + ((size_t)co * a.cin_total + ci0 + i) * ntaps + tap, v[i]);
+                        if (co0 + i < a.cout)
+                            atomicAdd(a.dw + (((size_t)(co0 + i) * a.cin_total + ci) * a.ks + r) * a.ks + s_tap, v[i]);
                 }
             }
         }
@@ -209,6 +215,8 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     a.two_boxes = cout > 64;
     const int cout_pad = (cout + 15) / 16 * 16;
     a.a_ch = cout_pad >= 64 ? 64 : (cout_pad % 32 == 0 ? 32 : 16);
+    a.n_co = cout_pad >= 128 ? 128 : cout_pad;
+    if (a.n_co != 16 && a.n_co != 32 && a.n_co != 64 && a.n_co != 128) return UAPS_ERANGE;   // 48/80/96/112: not a UNet_UAPS shape
     if (dy_c_stride < a.a_ch) return UAPS_ERANGE;                            // the dY box must lie inside the tensor's channels
     a.dw = dw;
     if (cin_pad != cin) return UAPS_ERANGE;                                  // callers pad Cin=3 layers on their side (see conv.py)
@@ -219,7 +227,7 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     // split-K: enough CTAs to fill the machine (as many as fit per SM by shared memory and the 512 TMEM columns),
     // but at least 4 pixel tiles per CTA so the 9 * n_chunk * Cout reductions of the epilogue stay amortised
     int tmem_cols = 32;
-    while (tmem_cols < ks * ks * a.n_chunk) tmem_cols <<= 1;
+    while (tmem_cols < ks * a.n_co) tmem_cols <<= 1;
     int per_sm = (int)((227 * 1024) / (smem + 2048));
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
     if (per_sm > 4) per_sm = 4;
@@ -228,7 +236,7 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     // cout * cin * taps of them; measured ~125 reductions/ns chip-wide) -- evaluate a simple cost model
     const int slots = per_sm * device_info().sm_count;
     const int groups = n_chunks * m_tiles;
-    const double tile_us = 1500.0 / 1900.0;                                  // ~1500 cycles per pixel tile (MMA issue bound)
+    const double tile_us = (12.0 * a.n_co + 300.0) / 1900.0;                 // tensor time 12 * Cout cycles per pixel tile + issue
     const double red_per_split_us = (double)cout * cin * ks * ks / 125e3;
     int best = 1;
     double best_t = 1e30;
