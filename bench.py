@@ -316,7 +316,7 @@ def run_ours(args):
             "e2e": {"value": N * world * e2e_steps / (ms_e2e * 1e-3), "unit": "pixels/s",
                     "h2d_bytes_per_step": 4 * K * C * N, "d2h_bytes_per_step": 12, "steps": e2e_steps,
                     "api": "uaps_b200.losses.uaps_unlabeled_loss + backward, pinned host logits"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 4 * args.steps,          # pass1, fold, finalize, pass2 per step
             "clocks": clocks,
         }
         if world == 1:

@@ -207,18 +207,23 @@ int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float* gamma, c
  * Output: bf16 NHWC with channel pitch out_c_stride, or fp32 NCHW (out_nchw_f32 = 1, the layout the
  * fused loss kernel consumes).  bias: fp32 [cout] or NULL.
  * ------------------------------------------------------------------------------------------- */
-size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks);
+/* fold = F in {1, 2, 4}: pixel folding.  F horizontally adjacent pixels of a small-channel tensor are viewed as
+ * one pixel with F*C channels (the same memory); the kernel runs the equivalent convolution with F*Cin input and
+ * F*Cout output channels and block-banded weights.  F times the MACs (these layers are bandwidth bound) for F
+ * times wider TMA rows -- the 16/32-channel layers are otherwise limited by TMA's per-row rate.  Needs W % F == 0
+ * and channel pitches equal to the channel counts rounded up to 16; all other arguments stay the REAL sizes. */
+size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks, int fold);
 /* w: device fp32 in torch layout [cout][cin1+cin2][ks][ks]; transpose = 1 packs the data-gradient
  * kernel W'[ci][co][r][s] = W[co][ci][ks-1-r][ks-1-s] (then cout/cin name W's input/output channels
  * swapped: pass cout = W's Cin, cin1 = W's Cout). */
 int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks,
-                           int transpose, cudaStream_t stream);
+                           int transpose, int fold, cudaStream_t stream);
 /* out2 (nullable): second bf16 NHWC output; output channels >= split (a multiple of 16) are written there
  * at channel (c - split) -- the data gradient of a concat convolution lands in its two consumers' tensors. */
 int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
                     const float* bias, void* out, int out_c_stride, int out_nchw_f32,
                     int B, int H, int W, int cin1, int cin2, int cout, int ks,
-                    void* out2, int out2_c_stride, int split, cudaStream_t stream);
+                    void* out2, int out2_c_stride, int split, int fold, cudaStream_t stream);
 
 /* Weight gradient on tcgen05 (MN-major operands straight from the channels-last tensors):
  * dw[co][ci_offset + ci][r][s] += sum_pixels dy[p][co] * x[p + (r-1, s-1)][ci].  dw is fp32 in torch layout

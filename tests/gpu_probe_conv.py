@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
-from uaps_b200.conv import PackedConv, to_nhwc_bf16
+from uaps_b200.conv import PackedConv, pick_fold, to_nhwc_bf16
 
 def timeit(fn, iters=20):
     for _ in range(3): fn()
@@ -19,7 +19,8 @@ def run(B, H, W, ci, co, ks, split=None, name=""):
     x = torch.randn(B, ci, H, W, device=dev)
     w = torch.randn(co, ci, ks, ks, device=dev) * 0.05
     b = torch.randn(co, device=dev)
-    conv = PackedConv(w, b, cin_split=split)
+    fold = pick_fold([ci] if split is None else [split, ci - split], co, ks, W)
+    conv = PackedConv(w, b, cin_split=split, fold=fold)
     if split is None:
         xs = (to_nhwc_bf16(x),)
     else:
@@ -31,7 +32,7 @@ def run(B, H, W, ci, co, ks, split=None, name=""):
     t_cudnn = timeit(lambda: F.conv2d(xc, wc, bc, padding=ks // 2))
     flop = 2.0 * B * H * W * co * ci * ks * ks
     byts = B * H * W * (max(ci, 16) + max(co, 16)) * 2
-    print(f"{name:14s} B={B} {H}x{W} {ci}->{co} k{ks}: ours {t_ours*1e3:8.1f}us {flop/t_ours/1e9:8.1f} TF/s {byts/t_ours/1e6:7.0f} GB/s | "
+    print(f"{name:14s} F={fold} B={B} {H}x{W} {ci}->{co} k{ks}: ours {t_ours*1e3:8.1f}us {flop/t_ours/1e9:8.1f} TF/s {byts/t_ours/1e6:7.0f} GB/s | "
           f"cuDNN {t_cudnn*1e3:8.1f}us {flop/t_cudnn/1e9:8.1f} TF/s | speedup {t_cudnn/t_ours:5.2f}x", flush=True)
 
 if __name__ == "__main__":

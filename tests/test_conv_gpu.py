@@ -139,3 +139,47 @@ def test_split_outputs_of_concat_data_gradient():
         a, b = conv(to_nhwc_bf16(dy), split=c)
         assert a.shape[-1] == c and b.shape[-1] == c
         assert torch.equal(a, whole[..., :c]) and torch.equal(b, whole[..., c:])
+
+
+@pytest.mark.parametrize("B,H,W,ci,co,ks,fold", [
+    (2, 64, 64, 16, 16, 3, 4), (2, 64, 64, 3, 16, 3, 4), (2, 32, 64, 16, 32, 3, 2), (2, 32, 32, 32, 32, 3, 2),
+    (1, 32, 64, 32, 64, 3, 2), (2, 64, 64, 32, 16, 1, 2), (2, 48, 96, 16, 16, 3, 4), (1, 16, 32, 16, 16, 3, 4),
+])
+def test_pixel_folded_conv_matches_torch(B, H, W, ci, co, ks, fold):
+    """Pixel folding (F pixels viewed as one pixel with F*C channels, block-banded weights) gives the same conv."""
+    from uaps_b200.conv import PackedConv, from_nhwc, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B + H + ci + co + fold)
+    x = torch.randn(B, ci, H, W, generator=g).to(dev)
+    w = (torch.randn(co, ci, ks, ks, generator=g) * (2.0 / (ci * ks * ks)) ** 0.5).to(dev)
+    b = torch.randn(co, generator=g).to(dev)
+    ref = _ref(x, w, b, ks)
+    out = from_nhwc(PackedConv(w, b, fold=fold)(to_nhwc_bf16(x)), co)
+    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    # and identical (up to accumulation order) to the unfolded kernel
+    plain = from_nhwc(PackedConv(w, b, fold=1)(to_nhwc_bf16(x)), co)
+    assert (out - plain).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+def test_pixel_folded_variants():
+    """Folded concat (two K segments), folded data gradient with split outputs, folded fp32-NCHW logits."""
+    from uaps_b200.conv import PackedConv, from_nhwc, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(31)
+    c = 16
+    skip, up = torch.randn(2, c, 32, 64, generator=g).to(dev), torch.randn(2, c, 32, 64, generator=g).to(dev)
+    w = (torch.randn(c, 2 * c, 3, 3, generator=g) * 0.06).to(dev)
+    b = torch.randn(c, generator=g).to(dev)
+    ref = _ref(torch.cat([skip, up], 1), w, b, 3)
+    out = from_nhwc(PackedConv(w, b, cin_split=c, fold=2)(to_nhwc_bf16(skip), to_nhwc_bf16(up)), c)
+    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    dy = torch.randn(2, c, 32, 64, generator=g).to(dev)
+    whole = PackedConv(w, None, transpose=True, fold=1)(to_nhwc_bf16(dy))
+    a, bb = PackedConv(w, None, transpose=True, fold=2)(to_nhwc_bf16(dy), split=c)
+    assert (a.float() - whole[..., :c].float()).abs().max().item() <= 2e-2 * whole.float().abs().max().item()
+    assert (bb.float() - whole[..., c:].float()).abs().max().item() <= 2e-2 * whole.float().abs().max().item()
+    x = torch.randn(2, 16, 32, 64, generator=g).to(dev)
+    wl, bl = (torch.randn(4, 16, 3, 3, generator=g) * 0.1).to(dev), torch.randn(4, generator=g).to(dev)
+    refl = _ref(x, wl, bl, 3)
+    outl = PackedConv(wl, bl, fold=4)(to_nhwc_bf16(x), out_nchw_f32=True)
+    assert outl.shape == refl.shape and (outl - refl).abs().max().item() <= 2e-3 * refl.abs().max().item()

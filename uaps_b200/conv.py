@@ -6,6 +6,7 @@ Activations are NHWC bf16 ("channels-last") with the channel count padded to a m
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -30,10 +31,32 @@ def from_nhwc(y: torch.Tensor, c: int) -> torch.Tensor:
     return y[..., :c].permute(0, 3, 1, 2).float().contiguous()
 
 
+# Pixel folding is implemented and parity-tested, but MEASURED SLOWER on B200 (enc0.conv2, B=64: 134 us folded F=4
+# vs 95 us unfolded; profiles/r01_conv_fold.txt): the folded layer needs 74 KB of resident weights (1 CTA/SM instead
+# of 4) and 4x the MMA and epilogue work per byte.  It stays off unless UAPS_CONV_FOLD=1.
+_FOLD_ENABLED = os.environ.get("UAPS_CONV_FOLD", "0") == "1"
+
+
+def pick_fold(cins, cout: int, ks: int, W: int) -> int:
+    """Pixel-folding factor for a conv whose K segments have `cins` channels: 4 for 16-channel tensors, 2 for
+    32-channel ones, when the folded layer still fits the kernel's resident-weight path (N' <= 128, <= 80 KB)."""
+    if not _FOLD_ENABLED:
+        return 1
+    cmax = max(pad16(c) for c in list(cins) + [cout])
+    for f in (4, 2):
+        if cmax * f > 64 or W % (8 * f) != 0:
+            continue
+        n_v, k_v = f * pad16(cout), sum(f * pad16(c) for c in cins)
+        if n_v <= 128 and ks * ks * n_v * k_v * 2 <= 80 * 1024:
+            return f
+    return 1
+
+
 class PackedConv:
     """Weights of one conv layer packed into the kernel's shared-memory stage image (bf16, pre-swizzled)."""
 
-    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], cin_split=None, transpose: bool = False):
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor], cin_split=None, transpose: bool = False,
+                 fold: int = 1):
         L.require_cuda(weight)
         w = weight.detach().float().contiguous()
         co, ci, ks, ks2 = w.shape
@@ -44,15 +67,19 @@ class PackedConv:
         else:
             self.cout = co
             self.cin1, self.cin2 = (ci, 0) if cin_split is None else (cin_split, ci - cin_split)
-        self.ks = ks
-        nbytes = L.lib().uaps_conv_packed_bytes(self.cout, self.cin1, self.cin2, ks)
+        self.ks, self.fold = ks, fold
+        nbytes = L.lib().uaps_conv_packed_bytes(self.cout, self.cin1, self.cin2, ks, fold)
         if nbytes == 0:
             raise RuntimeError("unsupported convolution shape")
         self.packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
         with torch.cuda.device(w.device):
             L.check(L.lib().uaps_conv_pack_weights(w.data_ptr(), self.packed.data_ptr(), self.cout, self.cin1, self.cin2,
-                                                   ks, int(transpose), L.stream_ptr()), "uaps_conv_pack_weights")
+                                                   ks, int(transpose), fold, L.stream_ptr()), "uaps_conv_pack_weights")
         self.bias = None if bias is None else bias.detach().float().contiguous()
+        if self.bias is not None and fold > 1:                # virtual bias: one padded copy per sub-pixel
+            b = torch.zeros(pad16(self.cout), dtype=torch.float32, device=w.device)
+            b[:self.cout] = self.bias
+            self.bias = b.repeat(fold).contiguous()
 
     def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, out_nchw_f32: bool = False,
                  split: int = 0):
@@ -69,15 +96,17 @@ class PackedConv:
             ocs = 0
         else:
             ocs = pad16(self.cout) if not split else split
-            alloc = torch.zeros if (ocs != self.cout and not split) else torch.empty
+            # folded kernels write the padding channels (zero weights -> zeros); unfolded ones mask them
+            alloc = torch.zeros if (ocs != self.cout and not split and self.fold == 1) else torch.empty
             out = alloc((B, H, W, ocs), dtype=torch.bfloat16, device=x1.device)
-        out2 = torch.empty((B, H, W, self.cout - split), dtype=torch.bfloat16, device=x1.device) if split else None
+        out2 = torch.empty((B, H, W, pad16(self.cout) - split), dtype=torch.bfloat16, device=x1.device) if split else None
         with torch.cuda.device(x1.device):
             L.check(L.lib().uaps_conv_fprop(x1.data_ptr(), c1s, None if x2 is None else x2.data_ptr(), c2s,
                                             self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(),
                                             out.data_ptr(), ocs, int(out_nchw_f32), B, H, W, self.cin1, self.cin2,
                                             self.cout, self.ks, None if out2 is None else out2.data_ptr(),
-                                            0 if out2 is None else self.cout - split, split, L.stream_ptr()), "uaps_conv_fprop")
+                                            0 if out2 is None else pad16(self.cout) - split, split, self.fold,
+                                            L.stream_ptr()), "uaps_conv_fprop")
         return out if not split else (out, out2)
 
 
@@ -131,13 +160,13 @@ class pack_scope:
         return False
 
 
-def packed(weight: torch.Tensor, bias, cin_split=None, transpose: bool = False) -> "PackedConv":
+def packed(weight: torch.Tensor, bias, cin_split=None, transpose: bool = False, fold: int = 1) -> "PackedConv":
     if _scope_depth == 0:
-        return PackedConv(weight, bias, cin_split=cin_split, transpose=transpose)
-    key = (id(weight), transpose, cin_split)
+        return PackedConv(weight, bias, cin_split=cin_split, transpose=transpose, fold=fold)
+    key = (id(weight), transpose, cin_split, fold)
     hit = _pack_cache.get(key)
     if hit is None:
-        hit = PackedConv(weight, bias, cin_split=cin_split, transpose=transpose)
+        hit = PackedConv(weight, bias, cin_split=cin_split, transpose=transpose, fold=fold)
         _pack_cache[key] = hit
     return hit
 
@@ -151,7 +180,9 @@ class _ConvFn(torch.autograd.Function):
         co, ci, ks, _ = weight.shape
         c1 = x1.shape[1]
         split = None if x2 is None else c1
-        conv = packed(weight, bias, cin_split=split)
+        W_img = x1.shape[3]
+        cins = [c1] if x2 is None else [c1, x2.shape[1]]
+        conv = packed(weight, bias, cin_split=split, fold=pick_fold(cins, co, ks, W_img))
         y = conv(_nhwc_view(x1), None if x2 is None else _nhwc_view(x2), out_nchw_f32=nchw_f32_out)
         ctx.save_for_backward(x1, x2, weight)
         ctx.has_bias, ctx.nchw, ctx.bias_grad = bias is not None, nchw_f32_out, bias_grad
@@ -172,12 +203,13 @@ class _ConvFn(torch.autograd.Function):
             gy_nhwc = pad
         # data gradient: tcgen05 kernel, W'[ci][co] rotated by 180 degrees
         c1 = x1.shape[1]
+        fold = pick_fold([co], ci if x2 is None else pad16(ci), ks, gy_nhwc.shape[2])
         if x2 is None:
-            gx = packed(weight, None, transpose=True)(gy_nhwc)          # [B,H,W,pad16(ci)]
+            gx = packed(weight, None, transpose=True, fold=fold)(gy_nhwc)   # [B,H,W,pad16(ci)]
             g1 = _as_cl(gx[..., :c1]) if ctx.needs_input_grad[0] else None
             g2 = None
         else:                                                            # concat conv: each consumer gets its own tensor
-            ga, gb2 = packed(weight, None, transpose=True)(gy_nhwc, split=c1)
+            ga, gb2 = packed(weight, None, transpose=True, fold=fold)(gy_nhwc, split=c1)
             g1 = _as_cl(ga) if ctx.needs_input_grad[0] else None
             g2 = _as_cl(gb2) if ctx.needs_input_grad[1] else None
         # weight gradient: tcgen05 kernel on the same channels-last tensors (MN-major operands, no transposes)

@@ -56,6 +56,9 @@ struct ConvArgs {
     void* out;
     void* out2;          // optional second NHWC output: channels >= split go there (data gradient of a concat conv)
     int split, out2_stride;
+    int fold;            // pixel folding factor F (1, 2, 4): the kernel sees [B,H,W/F,F*C] views; only the NCHW / split epilogues care
+    int cpp;             // output channels per real pixel in memory (pad16(cout_real))
+    int cout_real;
 };
 
 using namespace uaps::tc;
@@ -214,7 +217,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
 // whose packed weights fit in 64 KB keep them resident in shared memory: their stages carry only
 // activations, so a tile costs one A box per horizontal tap out of L2 and nothing else.
 constexpr int THREADS2 = 192;
-constexpr int W_RESIDENT_MAX = 64 * 1024;
+constexpr int W_RESIDENT_MAX = 80 * 1024;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -356,15 +359,24 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
                 }
                 if (!valid) continue;
                 if (a.out_nchw_f32) {
+                    // logits: fp32 NCHW of the REAL image; a folded column block is (sub-pixel, channel)
                     float* o = reinterpret_cast<float*>(a.out);
+                    const int sub = c0 / a.cpp, cb = c0 % a.cpp;
+                    const int xr = x * a.fold + sub, Wr = a.W * a.fold;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (c0 + i < a.cout) o[(((size_t)n_img * a.cout + c0 + i) * a.H + y) * a.W + x] = v[i];
+                        if (cb + i < a.cout_real) o[(((size_t)n_img * a.cout_real + cb + i) * a.H + y) * Wr + xr] = v[i];
                 } else {
                     const size_t pix = ((size_t)n_img * a.H + y) * a.W + x;
-                    __nv_bfloat16* o = (a.out2 != nullptr && c0 >= a.split)
-                        ? reinterpret_cast<__nv_bfloat16*>(a.out2) + pix * a.out2_stride + (c0 - a.split)
-                        : reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.cout_stride + c0;
+                    __nv_bfloat16* o;
+                    if (a.out2 != nullptr) {                       // concat data gradient: per real pixel, channels [0,split) | [split,cpp)
+                        const int sub = c0 / a.cpp, cb = c0 % a.cpp, rest = a.cpp - a.split;
+                        o = cb < a.split
+                            ? reinterpret_cast<__nv_bfloat16*>(a.out) + pix * (size_t)(a.fold * a.split) + sub * a.split + cb
+                            : reinterpret_cast<__nv_bfloat16*>(a.out2) + pix * (size_t)(a.fold * rest) + sub * rest + (cb - a.split);
+                    } else {
+                        o = reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.cout_stride + c0;
+                    }
                     if (c0 + 16 <= a.cout) {
                         uint32_t pk[8];
 #pragma unroll
@@ -397,13 +409,28 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
 // chunk (j ^ swz(n)) -- Swizzle<3|2|1,4,3> on the byte address, the pattern TMA / UMMA use.
 struct PackArgs {
     const float* w; unsigned char* dst;
-    int cout, cin_total, ks, n_tile, n_tiles, ck, nseg, seg_c[2], seg_pad[2];   // seg_pad: channels incl. zero padding
-    int transpose;       // 1: pack W'[ci][co][r][s] = W[co][ci][ks-1-r][ks-1-s] (data-gradient conv); cout/cin are those of W'
+    int cout_real, cin_total_real, ks, n_tile, n_tiles, ck, nseg;
+    int seg_real[2];     // channels of each K segment that have weights
+    int seg_mem[2];      // channels per pixel of each segment's tensor in memory (multiple of 16; zeros beyond seg_real)
+    int cout_mem;        // output channels per pixel in memory (pad16)
+    int fold;            // F: the virtual conv works on [.., W/F, F*C] views
+    int transpose;       // 1: logical W'[co][ci][r][s] = W[ci][co][ks-1-r][ks-1-s] (data-gradient conv)
 };
+// logical (unfolded) weight of the convolution being packed
+__device__ __forceinline__ float logical_w(const PackArgs& p, int co, int ci, int r, int s) {
+    if (!p.transpose) return p.w[(((size_t)co * p.cin_total_real + ci) * p.ks + r) * p.ks + s];
+    return p.w[(((size_t)ci * p.cout_real + co) * p.ks + (p.ks - 1 - r)) * p.ks + (p.ks - 1 - s)];
+}
+// Pixel folding: F horizontally adjacent pixels of a small-channel tensor are viewed as one pixel with F*C
+// channels (same memory).  The virtual conv has Cin' = F*Cin, Cout' = F*Cout and three horizontal taps dj over
+// folded pixels; virtual weight [(b,co)][(a,ci)][r][dj] = W[co][ci][r][s] with s = (dj-1)*F + a - b + 1 when
+// that is a real tap, else 0.  F x more MACs (free: these layers are bandwidth bound), F x wider TMA rows.
 __global__ void pack_weights_kernel(PackArgs p) {
+    const int F = p.fold;
     const int chunks_per_row = p.ck / 8;
-    const int chunks0 = p.seg_pad[0] / p.ck, chunks1 = p.nseg > 1 ? p.seg_pad[1] / p.ck : 0;
+    const int chunks0 = F * p.seg_mem[0] / p.ck, chunks1 = p.nseg > 1 ? F * p.seg_mem[1] / p.ck : 0;
     const int iters = (chunks0 + chunks1) * p.ks;
+    const int cout_v = F * p.cout_mem;
     const long long total = (long long)p.n_tiles * iters * p.ks * p.n_tile * chunks_per_row;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         long long t = idx;
@@ -412,22 +439,22 @@ __global__ void pack_weights_kernel(PackArgs p) {
         const int r = t % p.ks; t /= p.ks;
         const int it = t % iters; t /= iters;
         const int nt = (int)t;
-        const int s = it % p.ks;
+        const int dj = it % p.ks;
         int ch = it / p.ks, seg = 0;
         if (ch >= chunks0) { ch -= chunks0; seg = 1; }
-        const int co = nt * p.n_tile + n;
+        const int cov = nt * p.n_tile + n;                             // virtual output channel = (b, co)
+        const int b = cov / p.cout_mem, co = cov % p.cout_mem;
         const int span_rows = 128 / (p.ck * 2);                         // rows per 128 bytes: 1 / 2 / 4
         const int swz = (n / span_rows) % chunks_per_row;               // bits [7,7+B) of the byte address
         __nv_bfloat16 vals[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int cl = ch * p.ck + j * 8 + e;                       // channel inside the segment
+            const int clv = ch * p.ck + j * 8 + e;                      // virtual channel inside the segment = (a, cl)
+            const int a = clv / p.seg_mem[seg], cl = clv % p.seg_mem[seg];
+            const int s = p.ks == 3 ? (dj - 1) * F + a - b + 1 : (a == b ? 0 : -1);
             float v = 0.f;
-            if (co < p.cout && cl < p.seg_c[seg]) {
-                const int ci = (seg == 0 ? 0 : p.seg_c[0]) + cl;
-                if (!p.transpose) v = p.w[(((size_t)co * p.cin_total + ci) * p.ks + r) * p.ks + s];
-                else v = p.w[(((size_t)ci * p.cout + co) * p.ks + (p.ks - 1 - r)) * p.ks + (p.ks - 1 - s)];
-            }
+            if (cov < cout_v && co < p.cout_real && cl < p.seg_real[seg] && s >= 0 && s < p.ks)
+                v = logical_w(p, co, (seg == 0 ? 0 : p.seg_real[0]) + cl, r, s);
             vals[e] = __float2bfloat16_rn(v);
         }
         const size_t block = (((size_t)nt * iters + it) * p.ks + r) * p.n_tile * (p.ck * 2);
@@ -453,19 +480,21 @@ struct Plan {
     int ck, n_tile, n_tiles, seg_pad[2], chunks[2], nseg, iters;
     size_t packed_bytes;
 };
-// cin2 == 0: single segment.  Channels are zero-padded up to a multiple of 16 inside a segment.
-int make_plan(int cout, int cin1, int cin2, int ks, Plan* pl) {
-    if (cout <= 0 || cin1 <= 0 || cin2 < 0 || (ks != 1 && ks != 3)) return UAPS_EINVAL;
+// cin2 == 0: single segment.  Channels are zero-padded up to a multiple of 16 inside a segment; with pixel folding
+// (fold = F > 1) the plan is made for the virtual conv on the [.., W/F, F*C] views.
+int make_plan(int cout, int cin1, int cin2, int ks, int fold, Plan* pl) {
+    if (cout <= 0 || cin1 <= 0 || cin2 < 0 || (ks != 1 && ks != 3) || (fold != 1 && fold != 2 && fold != 4)) return UAPS_EINVAL;
     pl->nseg = cin2 > 0 ? 2 : 1;
-    pl->seg_pad[0] = (cin1 + 15) / 16 * 16;
-    pl->seg_pad[1] = (cin2 + 15) / 16 * 16;
+    pl->seg_pad[0] = fold * ((cin1 + 15) / 16 * 16);
+    pl->seg_pad[1] = fold * ((cin2 + 15) / 16 * 16);
     int ck = pick_ck(pl->seg_pad[0]);
     if (pl->nseg > 1) { const int ck2 = pick_ck(pl->seg_pad[1]); if (ck2 < ck) ck = ck2; }
     pl->ck = ck;
     pl->chunks[0] = pl->seg_pad[0] / ck;
     pl->chunks[1] = pl->nseg > 1 ? pl->seg_pad[1] / ck : 0;
-    pl->n_tile = pick_n_tile(cout);
-    pl->n_tiles = (cout + pl->n_tile - 1) / pl->n_tile;
+    const int cout_v = fold > 1 ? fold * ((cout + 15) / 16 * 16) : cout;
+    pl->n_tile = pick_n_tile(cout_v);
+    pl->n_tiles = (cout_v + pl->n_tile - 1) / pl->n_tile;
     pl->iters = (pl->chunks[0] + pl->chunks[1]) * ks;
     pl->packed_bytes = (size_t)pl->n_tiles * pl->iters * ks * pl->n_tile * ck * 2;
     return UAPS_OK;
@@ -503,24 +532,27 @@ int encode_map(CUtensorMap* map, const void* ptr, int B, int H, int W, int C, in
 }
 }  // namespace
 
-UAPS_API size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks) {
+UAPS_API size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks, int fold) {
     Plan pl;
-    if (make_plan(cout, cin1, cin2, ks, &pl) != UAPS_OK) return 0;
+    if (make_plan(cout, cin1, cin2, ks, fold, &pl) != UAPS_OK) return 0;
     return pl.packed_bytes;
 }
 
 UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks, int transpose,
-                                    cudaStream_t stream) {
+                                    int fold, cudaStream_t stream) {
     Plan pl;
-    int rc = make_plan(cout, cin1, cin2, ks, &pl);
+    int rc = make_plan(cout, cin1, cin2, ks, fold, &pl);
     if (rc != UAPS_OK) return rc;
     if (w == nullptr || w_packed == nullptr) return UAPS_EINVAL;
     if (!aligned_to(w_packed, 16)) return UAPS_EALIGN;
     PackArgs p{};
     p.w = w; p.dst = reinterpret_cast<unsigned char*>(w_packed);
-    p.cout = cout; p.cin_total = cin1 + cin2; p.ks = ks; p.n_tile = pl.n_tile; p.n_tiles = pl.n_tiles; p.ck = pl.ck;
-    p.nseg = pl.nseg; p.seg_c[0] = cin1; p.seg_c[1] = cin2; p.seg_pad[0] = pl.seg_pad[0]; p.seg_pad[1] = pl.seg_pad[1];
-    p.transpose = transpose;
+    p.cout_real = cout; p.cin_total_real = cin1 + cin2; p.ks = ks; p.n_tile = pl.n_tile; p.n_tiles = pl.n_tiles; p.ck = pl.ck;
+    p.nseg = pl.nseg; p.seg_real[0] = cin1; p.seg_real[1] = cin2;
+    p.seg_mem[0] = (cin1 + 15) / 16 * 16; p.seg_mem[1] = (cin2 + 15) / 16 * 16;
+    // unfolded outputs are addressed by real channel (stores beyond cout are masked); folded ones per padded pixel
+    p.cout_mem = fold > 1 ? (cout + 15) / 16 * 16 : pl.n_tiles * pl.n_tile;
+    p.fold = fold; p.transpose = transpose;
     const long long total = (long long)pl.packed_bytes / 16;
     const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     pack_weights_kernel<<<grid, 256, 0, stream>>>(p);
@@ -531,9 +563,20 @@ UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, in
 UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
                              const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
                              int cin1, int cin2, int cout, int ks, void* out2, int out2_c_stride, int split,
-                             cudaStream_t stream) {
+                             int fold, cudaStream_t stream) {
+    // fold = F > 1: run the virtual convolution on the [B, H, W/F, F*C] views of the same tensors.  Requires the
+    // tensors' channel pitch to equal their padded channel count (so F pixels are contiguous) and W % F == 0.
     Plan pl;
-    int rc = make_plan(cout, cin1, cin2, ks, &pl);
+    const int cout_real = cout, cpp = (cout + 15) / 16 * 16;
+    if (fold > 1) {
+        if (W % fold != 0 || c1_stride != (cin1 + 15) / 16 * 16 || (cin2 > 0 && c2_stride != (cin2 + 15) / 16 * 16)) return UAPS_ERANGE;
+        if (!out_nchw_f32 && out2 == nullptr && out_c_stride != cpp) return UAPS_ERANGE;
+    }
+    int rc = make_plan(cout, cin1, cin2, ks, fold, &pl);
+    if (rc == UAPS_OK && fold > 1) {                 // from here on: virtual sizes
+        W /= fold; c1_stride *= fold; c2_stride *= fold; out_c_stride *= fold;
+        cin1 = c1_stride; cin2 = cin2 > 0 ? c2_stride : 0; cout = fold * cpp;
+    }
     if (rc != UAPS_OK) return rc;
     if (x1 == nullptr || w_packed == nullptr || out == nullptr || B <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
     if (cin2 > 0 && x2 == nullptr) return UAPS_EINVAL;
@@ -542,7 +585,7 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
         return UAPS_ERANGE;
     if (!aligned_to(x1, 16) || (x2 && !aligned_to(x2, 16)) || !aligned_to(out, 16) || !aligned_to(w_packed, 16)) return UAPS_EALIGN;
     if (!out_nchw_f32 && (out_c_stride < (out2 != nullptr ? split : cout) || (out_c_stride % 8) != 0)) return UAPS_ERANGE;
-    if (out2 != nullptr && out2_c_stride < cout - split) return UAPS_ERANGE;
+    if (out2 != nullptr && out2_c_stride < cpp - split) return UAPS_ERANGE;
 
     ConvArgs a{};
     a.B = B; a.H = H; a.W = W; a.cout = cout; a.cout_stride = out_c_stride; a.n_tile = pl.n_tile; a.nseg = pl.nseg;
@@ -550,7 +593,8 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
     a.tiles_x = (W + TILE_W - 1) / TILE_W; a.tiles_y = (H + TILE_H - 1) / TILE_H;
     a.out_nchw_f32 = out_nchw_f32; a.bias = bias; a.w_packed = reinterpret_cast<const unsigned char*>(w_packed); a.out = out;
     a.out2 = out2; a.split = split; a.out2_stride = out2_c_stride;
-    if (out2 != nullptr && (out_nchw_f32 || (split % 16) != 0 || split <= 0 || split >= cout || (out2_c_stride % 8) != 0 ||
+    a.fold = fold; a.cpp = (fold > 1 || out2 != nullptr) ? cpp : cout; a.cout_real = cout_real;
+    if (out2 != nullptr && (out_nchw_f32 || (split % 16) != 0 || split <= 0 || split >= cpp || (out2_c_stride % 8) != 0 ||
                             !aligned_to(out2, 16) || getenv("UAPS_CONV_V1") != nullptr))
         return UAPS_EINVAL;
     const int row_bytes = pl.ck * 2;
