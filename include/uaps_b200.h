@@ -194,8 +194,9 @@ int uaps_bn_act_nhwc(const void* y, const double* sum, const double* sumsq, cons
                      float* save_mean, float* save_rstd, int64_t npix, int C, cudaStream_t stream);
 int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float* gamma, const float* beta,
                          const float* save_mean, const float* save_rstd, float slope, double p_drop,
-                         uint64_t seed, double* sum_g, double* sum_gx, void* dy, int64_t npix, int C,
-                         cudaStream_t stream);
+                         uint64_t seed, double* sum_g, double* sum_gx, void* dy,
+                         float* dgamma_accum, float* dbeta_accum, /* nullable pair: fp32 [C], += d gamma / d beta */
+                         int64_t npix, int C, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 / TMEM / TMA (3x3 pad 1 or 1x1, stride 1), bf16 operands, fp32

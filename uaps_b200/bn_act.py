@@ -6,6 +6,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
+from . import stepctx
 from .perturb import _next_seed
 
 
@@ -18,7 +19,8 @@ class _BnActFn(torch.autograd.Function):
         B, C, H, W = y.shape
         npix = B * H * W
         dev = y.device
-        sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        sc = stepctx.current()
+        sums = sc.take(2 * C) if sc is not None else torch.zeros(2 * C, dtype=torch.float64, device=dev)
         stats = torch.empty(2 * C, dtype=torch.float32, device=dev)          # save_mean | save_rstd
         out = torch.empty_like(y)
         lib = L.lib()
@@ -33,6 +35,7 @@ class _BnActFn(torch.autograd.Function):
                                          stats[C:].data_ptr(), npix, C, L.stream_ptr()), "uaps_bn_act_nhwc")
         ctx.save_for_backward(y, g32, b32, stats)
         ctx.cfg = (slope, p_drop, seed)
+        ctx.params = (gamma, beta)
         return out
 
     @staticmethod
@@ -43,13 +46,21 @@ class _BnActFn(torch.autograd.Function):
         g = g.contiguous(memory_format=torch.channels_last)
         if g.dtype != torch.bfloat16:
             g = g.to(torch.bfloat16)
-        sums = torch.zeros(2 * C, dtype=torch.float64, device=y.device)
+        sc = stepctx.current()
+        sums = sc.take(2 * C) if sc is not None else torch.zeros(2 * C, dtype=torch.float64, device=y.device)
         dy = torch.empty_like(y)
+        gamma, beta = ctx.params
+        direct = (sc is not None and sc.direct_grads and gamma.grad is not None and beta.grad is not None
+                  and gamma.grad.dtype == torch.float32 and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
         with torch.cuda.device(y.device):
             L.check(L.lib().uaps_bn_act_bwd_nhwc(g.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), stats.data_ptr(),
                                                  stats[C:].data_ptr(), slope, p_drop, seed, sums.data_ptr(),
-                                                 sums[C:].data_ptr(), dy.data_ptr(), B * H * W, C, L.stream_ptr()),
-                    "uaps_bn_act_bwd_nhwc")
+                                                 sums[C:].data_ptr(), dy.data_ptr(),
+                                                 gamma.grad.data_ptr() if direct else None,
+                                                 beta.grad.data_ptr() if direct else None,
+                                                 B * H * W, C, L.stream_ptr()), "uaps_bn_act_bwd_nhwc")
+        if direct:                               # already added into gamma.grad / beta.grad by the kernel
+            return dy, None, None, None, None, None, None, None, None, None
         return dy, sums[C:].float(), sums[:C].float(), None, None, None, None, None, None, None
 
 
@@ -62,5 +73,9 @@ def bn_lrelu_dropout(y: torch.Tensor, bn: torch.nn.BatchNorm2d, p_drop: float = 
     out = _BnActFn.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum), float(bn.eps),
                          float(slope), float(p_drop), 0 if seed is None else int(seed))
     if bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+        sc = stepctx.current()
+        if sc is not None:
+            sc.counters.append(bn.num_batches_tracked)      # one foreach add at the end of the iteration
+        else:
+            bn.num_batches_tracked += 1
     return out

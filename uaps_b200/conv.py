@@ -12,6 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib as L
+from . import stepctx
 
 
 def pad16(c: int) -> int:
@@ -110,11 +111,12 @@ class PackedConv:
         return out if not split else (out, out2)
 
 
-def conv_wgrad(dy_nhwc: torch.Tensor, xs, cout: int, cin_total: int, ks: int) -> torch.Tensor:
+def conv_wgrad(dy_nhwc: torch.Tensor, xs, cout: int, cin_total: int, ks: int, out: torch.Tensor = None) -> torch.Tensor:
     """dW (fp32, torch layout [cout][cin_total][ks][ks]) of a conv whose input is the channel concat of `xs`
-    (NHWC bf16 tensors, each a multiple of 16 channels) and whose output gradient is dy_nhwc."""
+    (NHWC bf16 tensors, each a multiple of 16 channels) and whose output gradient is dy_nhwc.  `out`: an fp32
+    tensor of that shape to ACCUMULATE into (e.g. the parameter's pre-zeroed .grad) instead of a fresh one."""
     B, H, W, dcs = dy_nhwc.shape
-    dw = torch.zeros((cout, cin_total, ks, ks), dtype=torch.float32, device=dy_nhwc.device)
+    dw = out if out is not None else torch.zeros((cout, cin_total, ks, ks), dtype=torch.float32, device=dy_nhwc.device)
     off = 0
     with torch.cuda.device(dy_nhwc.device):
         for x in xs:
@@ -186,6 +188,7 @@ class _ConvFn(torch.autograd.Function):
         y = conv(_nhwc_view(x1), None if x2 is None else _nhwc_view(x2), out_nchw_f32=nchw_f32_out)
         ctx.save_for_backward(x1, x2, weight)
         ctx.has_bias, ctx.nchw, ctx.bias_grad = bias is not None, nchw_f32_out, bias_grad
+        ctx.weight_param = weight
         return y if nchw_f32_out else _as_cl(y)
 
     @staticmethod
@@ -215,14 +218,25 @@ class _ConvFn(torch.autograd.Function):
         # weight gradient: tcgen05 kernel on the same channels-last tensors (MN-major operands, no transposes)
         xs = [_nhwc_view(x1)] + ([] if x2 is None else [_nhwc_view(x2)])
         cin_pad = sum(t.shape[3] for t in xs)                 # the 3-channel network input is stored 16-padded
-        gw = conv_wgrad(gy_nhwc, xs, co, cin_pad, ks)
-        if cin_pad != ci:
-            gw = gw[:, :ci].contiguous()
+        sc = stepctx.current()
+        wparam = ctx.weight_param
+        direct = (sc is not None and sc.direct_grads and cin_pad == ci and wparam.grad is not None
+                  and wparam.grad.dtype == torch.float32 and wparam.grad.is_contiguous())
+        if direct:                               # accumulate straight into the pre-zeroed .grad view
+            conv_wgrad(gy_nhwc, xs, co, cin_pad, ks, out=wparam.grad)
+            gw = None
+        else:
+            gw = conv_wgrad(gy_nhwc, xs, co, cin_pad, ks)
+            if cin_pad != ci:
+                gw = gw[:, :ci].contiguous()
         gb = None
         if ctx.has_bias:
             # a bias in front of train-mode BatchNorm has an analytically zero gradient; only conv1x1 /
             # out_conv (bias_grad=True) need the reduction
-            gb = gy.float().sum(dim=(0, 2, 3)) if ctx.bias_grad else torch.zeros(co, dtype=torch.float32, device=gy.device)
+            if ctx.bias_grad:
+                gb = gy.float().sum(dim=(0, 2, 3))
+            elif not direct:
+                gb = torch.zeros(co, dtype=torch.float32, device=gy.device)
         return g1, g2, gw, gb, None, None
 
 

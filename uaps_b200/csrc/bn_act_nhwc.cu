@@ -92,6 +92,7 @@ struct BnParams {
     uint64_t seed;
     long long npix;
     int G;
+    float* dgamma_accum; float* dbeta_accum;      // backward: optional fp32 gradient buffers to accumulate into
 };
 
 // forward: a = dropout(leaky_relu(gamma * (y - mean) * rstd + beta))
@@ -174,6 +175,12 @@ __global__ void __launch_bounds__(BT) bn_act_bwd_reduce_kernel(const uint4* __re
 // dy = gamma * rstd * (g' - mean(g') - xhat * mean(g' * xhat))
 __global__ void __launch_bounds__(BT) bn_act_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
                                                         uint4* __restrict__ dy, const BnParams p) {
+    if (blockIdx.x == 0 && p.dgamma_accum != nullptr) {       // d gamma = sum(g' * xhat), d beta = sum(g'): add to .grad
+        for (int c = threadIdx.x; c < 8 * p.G; c += BT) {
+            p.dgamma_accum[c] += (float)p.sumsq[c];
+            p.dbeta_accum[c] += (float)p.sum[c];
+        }
+    }
     const int chunk = threadIdx.x % p.G;
     const float invn = (float)(1.0 / (double)p.npix);
     float mean[8], rstd[8], ga[8], be[8], mg[8], mgx[8];
@@ -241,7 +248,8 @@ UAPS_API int uaps_bn_act_nhwc(const void* y, const double* sum, const double* su
 
 UAPS_API int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float* gamma, const float* beta, const float* save_mean,
                                   const float* save_rstd, float slope, double p_drop, uint64_t seed, double* sum_g,
-                                  double* sum_gx, void* dy, int64_t npix, int C, cudaStream_t stream) {
+                                  double* sum_gx, void* dy, float* dgamma_accum, float* dbeta_accum, int64_t npix, int C,
+                                  cudaStream_t stream) {
     if (g_out == nullptr || y == nullptr || gamma == nullptr || beta == nullptr || save_mean == nullptr || save_rstd == nullptr ||
         sum_g == nullptr || sum_gx == nullptr || dy == nullptr || npix <= 0)
         return UAPS_EINVAL;
@@ -251,6 +259,8 @@ UAPS_API int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float*
     p.sum = sum_g; p.sumsq = sum_gx; p.gamma = gamma; p.beta = beta; p.save_mean = const_cast<float*>(save_mean);
     p.save_rstd = const_cast<float*>(save_rstd); p.slope = slope; p.p = (float)p_drop;
     p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
+    if ((dgamma_accum == nullptr) != (dbeta_accum == nullptr)) return UAPS_EINVAL;
+    p.dgamma_accum = dgamma_accum; p.dbeta_accum = dbeta_accum;
     const int grid = bn_grid(npix * (C / 8));
     // sum_g / sum_gx (zeroed by the caller) receive sum(g') and sum(g' * xhat) = d beta and d gamma
     bn_act_bwd_reduce_kernel<<<bn_grid(npix * (C / 8), 4), BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y), p,

@@ -25,6 +25,7 @@ import torch
 import torch.distributed as dist
 
 from .conv import pack_scope
+from .stepctx import StepContext
 from .losses import uaps_supervised_loss, uaps_unlabeled_loss
 from .ramps import get_current_consistency_weight
 
@@ -80,7 +81,7 @@ class UAPSTrainer:
     def step(self, x_l: torch.Tensor, y_l: torch.Tensor, x_u: torch.Tensor,
              mix_w=None, rand_l=None, rand_u=None) -> Dict[str, torch.Tensor]:
         self.model.train()
-        with pack_scope():                                   # conv weights packed once for the whole iteration
+        with pack_scope(), StepContext(x_l.device):          # weights packed once; gradients accumulated in place
             out_l = self.model(x_l) if rand_l is None else self.model(x_l, rand=rand_l)         # :177
             out_u = self.model(x_u) if rand_u is None else self.model(x_u, rand=rand_u)         # :185
             sup, tce, tdice, ce_k = uaps_supervised_loss(out_l, y_l, group=self.group)           # :194-218
