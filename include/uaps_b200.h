@@ -234,6 +234,12 @@ int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int x_c_stri
                     int B, int H, int W, int cout, int cin, int cin_total, int ci_offset, int ks,
                     cudaStream_t stream);
 
+/* On-device confusion matrix behind utilities/metrics.py (pixel_accuracy :8, mIoU :16, mDice :40):
+ * conf[label * C + argmax(softmax(logits))] += 1 per pixel (labels outside [0,C) ignored).  logits [B,C,HW] fp32,
+ * labels [B,HW] int64, conf C*C uint64 ACCUMULATED into. */
+int uaps_confusion(const float* logits, const int64_t* labels, int B, int C, int64_t HW, uint64_t* conf,
+                   cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

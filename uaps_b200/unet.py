@@ -177,6 +177,14 @@ class UNet_UAPS(nn.Module):
             outs.append(self._decode16(pf, self.get_submodule(f"aux_decoder{a}")))
         return tuple(outs) if self.n_aux else outs[0]
 
+    @torch.no_grad()
+    def predict(self, x: torch.Tensor) -> torch.Tensor:
+        """Validation / inference fast path (UAPS_train.py:377, UAPS-Testing.ipynb): the main decoder's logits only.
+        The reference runs -- and perturbs -- all three auxiliary decoders here and throws their outputs away."""
+        if self.compute == "bf16":
+            return self._decode16(self._encode16(x, None), self.main_decoder)
+        return self.decode(self.encode(x), self.main_decoder)
+
     def decoders(self) -> List[nn.Module]:
         return [self.main_decoder] + [self.get_submodule(f"aux_decoder{a}") for a in range(1, self.n_aux + 1)]
 
@@ -216,6 +224,23 @@ def load_reference_state_dict(model: nn.Module, state_dict: Dict[str, torch.Tens
     ``module.`` prefix that ``nn.DataParallel`` (UAPS_model.py:13) puts on every key."""
     cleaned = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in state_dict.items()}
     return model.load_state_dict(cleaned, strict=strict)
+
+
+def save_checkpoint(path: str, model: nn.Module, optimizer, epoch: int, best_dice: float, data_parallel_keys: bool = True):
+    """The reference's checkpoint dict (UAPS_train.py:443-450): {"epoch", "best_dice_1", "state_dict", "optimizer"},
+    with the ``module.`` key prefix its DataParallel wrapper produces, so the reference's notebooks can load it."""
+    sd = model.state_dict()
+    if data_parallel_keys:
+        sd = {"module." + k: v for k, v in sd.items()}
+    torch.save({"epoch": epoch, "best_dice_1": best_dice, "state_dict": sd, "optimizer": optimizer.state_dict()}, path)
+
+
+def load_checkpoint(path: str, model: nn.Module, optimizer=None, map_location=None):
+    ck = torch.load(path, map_location=map_location)
+    load_reference_state_dict(model, ck["state_dict"])
+    if optimizer is not None and "optimizer" in ck:
+        optimizer.load_state_dict(ck["optimizer"])
+    return ck.get("epoch"), ck.get("best_dice_1")
 
 
 def net_factory(net_type: str = "unet_uaps", in_chns: int = 3, class_num: int = 4):
