@@ -209,12 +209,16 @@ def run_ours(args):
 
     def step(ev=None):
         if ev: ev[0].record()
-        L.check(lib.uaps_loss_pass1(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0, st), "pass1")
-        if ev: ev[1].record()
-        if world > 1:
+        if world == 1:          # single rank: fold + finalize fused into one launch behind pass 1
+            L.check(lib.uaps_loss_pass1_scalars(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0,
+                                                CW1, CW2, sc.data_ptr(), st), "pass1")
+            if ev: ev[1].record(); ev[2].record()
+        else:
+            L.check(lib.uaps_loss_pass1(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0, st), "pass1")
+            if ev: ev[1].record()
             dist.all_reduce(sums, group=group)
-        L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, N * world, CW1, CW2, 0, sc.data_ptr(), st), "finalize")
-        if ev: ev[2].record()
+            L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, N * world, CW1, CW2, 0, sc.data_ptr(), st), "finalize")
+            if ev: ev[2].record()
         L.check(lib.uaps_loss_pass2(zp, K, B, C, H * W, w_arr, None, sc.data_ptr(), go.data_ptr(), dzp, 0, st), "pass2")
         if ev: ev[3].record()
 
@@ -316,7 +320,7 @@ def run_ours(args):
             "e2e": {"value": N * world * e2e_steps / (ms_e2e * 1e-3), "unit": "pixels/s",
                     "h2d_bytes_per_step": 4 * K * C * N, "d2h_bytes_per_step": 12, "steps": e2e_steps,
                     "api": "uaps_b200.losses.uaps_unlabeled_loss + backward, pinned host logits"},
-            "gpu_launches": 4 * args.steps,          # pass1, fold, finalize, pass2 per step
+            "gpu_launches": (3 if world == 1 else 4) * args.steps,   # pass1, fold(+finalize), [finalize], pass2 per step
             "clocks": clocks,
         }
         if world == 1:
@@ -349,8 +353,8 @@ def loss_sweep(dev, lib, L, iters: int = 10):
         n = b * h * w
 
         def step():
-            L.check(lib.uaps_loss_pass1(zp, k, b, c, h * w, wa, None, ws.data_ptr(), sums.data_ptr(), None, None, 0, st), "p1")
-            L.check(lib.uaps_loss_finalize(sums.data_ptr(), k, c, n, CW1, CW2, 0, sc.data_ptr(), st), "fin")
+            L.check(lib.uaps_loss_pass1_scalars(zp, k, b, c, h * w, wa, None, ws.data_ptr(), sums.data_ptr(), None, None, 0,
+                                                CW1, CW2, sc.data_ptr(), st), "p1")
             L.check(lib.uaps_loss_pass2(zp, k, b, c, h * w, wa, None, sc.data_ptr(), go.data_ptr(), dzp, 0, st), "p2")
         for _ in range(3):
             step()

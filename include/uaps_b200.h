@@ -99,6 +99,13 @@ int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t HW,
                     void* workspace, double* sums,
                     int64_t* pseudo_out, float* const* exp_var_out, int flags, cudaStream_t stream);
 
+/* Single-rank fast path: pass 1 followed by ONE kernel that folds the partial sums and writes the scalars
+ * (N_global = B * HW), i.e. uaps_loss_pass1 + uaps_loss_finalize with a launch less.  `sums` is still written. */
+int uaps_loss_pass1_scalars(const float* const* z, int K, int B, int C, int64_t HW,
+                            const float* mix_w, const int64_t* labels, void* workspace, double* sums,
+                            int64_t* pseudo_out, float* const* exp_var_out, int flags,
+                            float cw1, float cw2, float* scalars, cudaStream_t stream);
+
 /* sums_global: device, uaps_loss_sums_count doubles (all-reduced over ranks by the caller when
  * the batch is sharded); N_global = total pixels behind those sums.  supervised != 0 selects
  * the labeled-batch formula (scalars[LOSS_U] = mean_k 0.5(CE_k + Dice_k), cw ignored). */

@@ -87,9 +87,10 @@ UAPS_API size_t uaps_loss_workspace_bytes(int K, int C) {
     return WS_HEADER_BYTES + (size_t)LOSS_MAX_BLOCKS * sums_count(K, C) * sizeof(float);   // partials[S][MAX_BLOCKS]
 }
 
-UAPS_API int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t HW,
+static int loss_pass1_impl(const float* const* z, int K, int B, int C, int64_t HW,
                                const float* mix_w, const int64_t* labels, void* workspace, double* sums,
-                               int64_t* pseudo_out, float* const* exp_var_out, int flags, cudaStream_t stream) {
+                               int64_t* pseudo_out, float* const* exp_var_out, int flags, cudaStream_t stream,
+                          int64_t N_global, float cw1, float cw2, float* scalars) {
     int rc = check_common(z, K, B, C, HW, mix_w, labels);
     if (rc != UAPS_OK) return rc;
     if (workspace == nullptr || sums == nullptr) return UAPS_EINVAL;
@@ -112,10 +113,32 @@ UAPS_API int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t
     rc = dispatch_k(K, C, impl, labels != nullptr, false, a, partials, nullptr, nullptr, &nblocks, stream);
     if (rc != UAPS_OK) return rc;
     const int S = sums_count(K, C);
-    loss_fold_kernel<<<ceil_div(S, 256 / kWarp), 256, 0, stream>>>(partials, S, (unsigned)nblocks, sums);
+    if (scalars != nullptr)
+        loss_fold_finalize_kernel<<<1, 1024, 0, stream>>>(partials, S, (unsigned)nblocks, sums, K, C, (double)N_global, cw1, cw2,
+                                                          labels != nullptr, scalars);
+    else
+        loss_fold_kernel<<<ceil_div(S, 256 / kWarp), 256, 0, stream>>>(partials, S, (unsigned)nblocks, sums);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
+
+UAPS_API int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t HW, const float* mix_w,
+                             const int64_t* labels, void* workspace, double* sums, int64_t* pseudo_out,
+                             float* const* exp_var_out, int flags, cudaStream_t stream) {
+    return loss_pass1_impl(z, K, B, C, HW, mix_w, labels, workspace, sums, pseudo_out, exp_var_out, flags, stream, 0, 0.f, 0.f,
+                           nullptr);
+}
+
+// pass 1 + fused fold/finalize: the single-rank path (no exchange between the passes), one launch fewer
+UAPS_API int uaps_loss_pass1_scalars(const float* const* z, int K, int B, int C, int64_t HW, const float* mix_w,
+                                     const int64_t* labels, void* workspace, double* sums, int64_t* pseudo_out,
+                                     float* const* exp_var_out, int flags, float cw1, float cw2, float* scalars,
+                                     cudaStream_t stream) {
+    if (scalars == nullptr || !aligned_to(scalars, 4)) return UAPS_EINVAL;
+    return loss_pass1_impl(z, K, B, C, HW, mix_w, labels, workspace, sums, pseudo_out, exp_var_out, flags, stream,
+                           (int64_t)B * HW, cw1, cw2, scalars);
+}
+
 
 UAPS_API int uaps_loss_finalize(const double* sums_global, int K, int C, int64_t N_global, float cw1,
                                   float cw2, int supervised, float* scalars, cudaStream_t stream) {

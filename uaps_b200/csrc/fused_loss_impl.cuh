@@ -101,7 +101,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kTieMargin = 2e-5f;
 constexpr float kLg2Floor = -120.0f;     // below this exp2 underflows (ftz): take log2 p from t - log2(sum) instead
 
-template <int C>
+template <int C, bool TRACK_MIN>
 __device__ __forceinline__ float softmax_fast(const float (&z)[C], float (&p)[C], float (&l2)[C]) {
     float m = z[0];
 #pragma unroll
@@ -112,7 +112,7 @@ __device__ __forceinline__ float softmax_fast(const float (&z)[C], float (&p)[C]
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const float t = fmaf(z[c], kLog2e, nm);
-        tmin = fminf(tmin, t);
+        if constexpr (TRACK_MIN) tmin = fminf(tmin, t);
         e[c] = ex2_approx(t);
         s += e[c];
     }
@@ -138,7 +138,7 @@ __device__ __forceinline__ void log2_softmax_underflow_fix(const float (&z)[C], 
     const float l2s = lg2_approx(s);
 #pragma unroll
     for (int c = 0; c < C; ++c)
-        if (t[c] < kLg2Floor) l2[c] = t[c] - l2s;
+        if (t[c] < kLg2Floor) l2[c] = t[c] - l2s;      // lg2(p) is exact enough above the floor; below it p may have flushed
 }
 
 // torch-order argmax of the Dirichlet mix (UAPS_train.py:251-255), every rounding reproduced
@@ -172,72 +172,91 @@ __device__ __noinline__ int argmax_exact_gmem(const LossArgs& a, size_t pix_off)
     return argmax_exact<K, C>(p, w);
 }
 
+// mean prediction (UAPS_train.py:223) and KL maps (:226-236): V_k = sum_c xlogy(q,q) - q * l_kc, E_k = exp(-V_k).
+// GUARD: apply xlogy's q == 0 -> 0 rule explicitly (the fast path leaves it to the NaN check of its caller).
+template <int K, int C, bool EXACT, bool GUARD>
+__device__ __forceinline__ void kl_terms(PixelState<K, C>& st) {
+    constexpr float U = LogUnit<EXACT>::U;
+    float h = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float acc = st.p[0][c];
+#pragma unroll
+        for (int k = 1; k < K; ++k) acc = __fadd_rn(acc, st.p[k][c]);
+        const float q = acc * (1.0f / K);
+        st.q[c] = q;
+        st.lq[c] = EXACT ? logf(q) : lg2_approx(q);
+        if constexpr (GUARD) h += (q == 0.f) ? 0.f : q * st.lq[c];
+        else h = fmaf(q, st.lq[c], h);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) d = fmaf(st.q[c], st.l[k][c], d);
+        st.V[k] = (h - d) * U;
+        st.E[k] = EXACT ? expf(-st.V[k]) : ex2_approx(-kLog2e * st.V[k]);
+    }
+}
+
 template <int K, int C, bool SUP, bool EXACT>
 __device__ __forceinline__ void pixel_forward(const float (&z)[K][C], const float (&w)[K], int label,
                                               const LossArgs& a, size_t pix_off, PixelState<K, C>& st) {
-    constexpr float U = LogUnit<EXACT>::U;
-    float tmin = 0.f;
+    if constexpr (EXACT) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        if constexpr (EXACT) softmax_exact<C>(z[k], st.p[k], st.l[k]);
-        else tmin = fminf(tmin, softmax_fast<C>(z[k], st.p[k], st.l[k]));
-    }
-    if constexpr (SUP) {
-        if constexpr (!EXACT) {
-            if (__builtin_expect(tmin < kLg2Floor, 0)) {
+        for (int k = 0; k < K; ++k) softmax_exact<C>(z[k], st.p[k], st.l[k]);
+        if constexpr (SUP) {
+            st.y = label;
 #pragma unroll
-                for (int k = 0; k < K; ++k) log2_softmax_underflow_fix<C>(z[k], st.l[k]);
-            }
+            for (int k = 0; k < K; ++k) { st.V[k] = 0.f; st.E[k] = 1.f; }
+        } else {
+            st.y = argmax_exact<K, C>(st.p, w);
+            kl_terms<K, C, true, true>(st);
+        }
+    } else if constexpr (SUP) {
+        float tmin = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) tmin = fminf(tmin, softmax_fast<C, true>(z[k], st.p[k], st.l[k]));
+        if (__builtin_expect(tmin < kLg2Floor, 0)) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) log2_softmax_underflow_fix<C>(z[k], st.l[k]);
         }
         st.y = label;
 #pragma unroll
         for (int k = 0; k < K; ++k) { st.V[k] = 0.f; st.E[k] = 1.f; }
-        return;
     } else {
-        if constexpr (EXACT) {
-            st.y = argmax_exact<K, C>(st.p, w);
-        } else {
-            int y = 0;
-            float best = 0.f, second = -1.f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float mix = w[0] * st.p[0][c];
-#pragma unroll
-                for (int k = 1; k < K; ++k) mix = fmaf(w[k], st.p[k][c], mix);
-                if (c == 0) best = mix;
-                else if (mix > best) { second = best; best = mix; y = c; }
-                else second = fmaxf(second, mix);
-            }
-            // one rarely-taken branch per pixel covers both slow paths
-            if (__builtin_expect(!(best - second > kTieMargin) || tmin < kLg2Floor, 0)) {
-                if (!(best - second > kTieMargin)) y = argmax_exact_gmem<K, C>(a, pix_off);
-                if (tmin < kLg2Floor) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) log2_softmax_underflow_fix<C>(z[k], st.l[k]);
-                }
-            }
-            st.y = y;
-        }
-        // mean prediction (:223) and KL maps (:226-236): V_k = sum_c xlogy(q,q) - q * l_kc
-        float h = 0.f;
+        for (int k = 0; k < K; ++k) softmax_fast<C, false>(z[k], st.p[k], st.l[k]);
+        // Dirichlet mix + argmax (:251-255) with the runner-up, to know when the fast value can be trusted
+        int y = 0;
+        float best = 0.f, second = -1.f;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            float acc = st.p[0][c];
+            float mix = w[0] * st.p[0][c];
 #pragma unroll
-            for (int k = 1; k < K; ++k) acc = __fadd_rn(acc, st.p[k][c]);
-            const float q = acc * (1.0f / K);
-            st.q[c] = q;
-            st.lq[c] = EXACT ? logf(q) : lg2_approx(q);
-            h += (q == 0.f) ? 0.f : q * st.lq[c];
+            for (int k = 1; k < K; ++k) mix = fmaf(w[k], st.p[k][c], mix);
+            if (c == 0) best = mix;
+            else if (mix > best) { second = best; best = mix; y = c; }
+            else second = fmaxf(second, mix);
         }
+        kl_terms<K, C, false, false>(st);
+        // An underflowed probability (p flushed to 0 -> log2 p = -inf) always surfaces as a non-finite V:
+        // q_c > 0 gives V = +inf, q_c == 0 gives 0 * -inf = NaN.  One rarely-taken branch per pixel covers
+        // both slow paths: near-tie -> exact argmax; non-finite -> logs from (z - max) and xlogy's 0 rule.
+        float vs = st.V[0];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            float d = 0.f;
+        for (int k = 1; k < K; ++k) vs += st.V[k];
+        const bool tie = !(best - second > kTieMargin);
+        const bool bad = !(fabsf(vs) < 1e30f);
+        if (__builtin_expect(tie || bad, 0)) {
+            if (tie) y = argmax_exact_gmem<K, C>(a, pix_off);
+            if (bad) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) d = fmaf(st.q[c], st.l[k][c], d);
-            st.V[k] = (h - d) * U;
-            st.E[k] = EXACT ? expf(-st.V[k]) : ex2_approx(-kLog2e * st.V[k]);
+                for (int k = 0; k < K; ++k) log2_softmax_underflow_fix<C>(z[k], st.l[k]);
+                kl_terms<K, C, false, true>(st);
+            }
         }
+        st.y = y;
     }
 }
 
@@ -402,9 +421,34 @@ __global__ void __launch_bounds__(256) loss_fold_kernel(const float* __restrict_
     if (lane == 0) sums[i] = r;
 }
 
-__global__ void loss_finalize_kernel(const double* __restrict__ sums, int K, int C, double N,
-                                     float cw1, float cw2, int supervised, float* __restrict__ sc) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Single-rank fast path: fold + finalize in one launch (one CTA of 32 warps, a warp per sum row, then thread 0
+// turns the sums into the scalars).  Saves a kernel and a launch gap per step versus fold -> finalize.
+__device__ void finalize_from_sums(const double* sums, int K, int C, double N, float cw1, float cw2, int supervised, float* sc);
+
+__global__ void __launch_bounds__(1024) loss_fold_finalize_kernel(const float* __restrict__ partials, int S, unsigned nblocks,
+                                                                   double* __restrict__ sums, int K, int C, double N, float cw1,
+                                                                   float cw2, int supervised, float* __restrict__ sc) {
+    __shared__ double s_sums[3 * KMAX + 2 * KMAX * CMAX + CMAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < S; i += 32) {
+        const float* row = partials + (size_t)i * LOSS_MAX_BLOCKS;
+        float v[LOSS_MAX_BLOCKS / kWarp];
+#pragma unroll
+        for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) {
+            const unsigned blk = u * kWarp + lane;
+            v[u] = (blk < nblocks) ? __ldcg(row + blk) : 0.f;
+        }
+        double r = 0.0;
+#pragma unroll
+        for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) r += (double)v[u];
+        r = warp_sum(r);
+        if (lane == 0) { s_sums[i] = r; sums[i] = r; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) finalize_from_sums(s_sums, K, C, N, cw1, cw2, supervised, sc);
+}
+
+__device__ void finalize_from_sums(const double* sums, int K, int C, double N, float cw1, float cw2, int supervised, float* sc) {
     const double* sCE = sums;
     const double* sE = sums + K;
     const double* sV = sums + 2 * K;
@@ -448,6 +492,11 @@ __global__ void loss_finalize_kernel(const double* __restrict__ sums, int K, int
     sc[UAPS_SC_MEAN_DICE] = (float)(mdi / K);                           // :217 total_loss_dice
 }
 
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, int K, int C, double N,
+                                     float cw1, float cw2, int supervised, float* __restrict__ sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    finalize_from_sums(sums, K, C, N, cw1, cw2, supervised, sc);
+}
 #endif  // UAPS_LOSS_ENTRY
 
 // ---- pass 2 --------------------------------------------------------------------------------

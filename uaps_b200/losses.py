@@ -90,15 +90,21 @@ class _FusedLossFn(torch.autograd.Function):
             exp_var = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(K)] \
                 if (want_exp_var and not sup) else None
             zp = L.ptr_array(zs)
-            L.check(lib.uaps_loss_pass1(zp, K, B, C, HW, w_arr, None if not sup else labels.data_ptr(),
-                                        _workspace(dev, K, C).data_ptr(), sums.data_ptr(),
-                                        None if pseudo is None else pseudo.data_ptr(),
-                                        None if exp_var is None else L.ptr_array(exp_var),
-                                        flags, L.stream_ptr()), "uaps_loss_pass1")
-            world = _allreduce_sums(sums, group)
-            n_tot = int(n_global) if n_global else B * HW * world
-            L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, n_tot, float(cw1), float(cw2), int(sup),
-                                           scalars.data_ptr(), L.stream_ptr()), "uaps_loss_finalize")
+            import torch.distributed as dist
+            single = (group is None or not dist.is_initialized() or dist.get_world_size(group) == 1) and not n_global
+            common = (zp, K, B, C, HW, w_arr, None if not sup else labels.data_ptr(),
+                      _workspace(dev, K, C).data_ptr(), sums.data_ptr(),
+                      None if pseudo is None else pseudo.data_ptr(),
+                      None if exp_var is None else L.ptr_array(exp_var), flags)
+            if single:                               # no exchange between the passes: fold + finalize fused
+                L.check(lib.uaps_loss_pass1_scalars(*common, float(cw1), float(cw2), scalars.data_ptr(), L.stream_ptr()),
+                        "uaps_loss_pass1_scalars")
+            else:
+                L.check(lib.uaps_loss_pass1(*common, L.stream_ptr()), "uaps_loss_pass1")
+                world = _allreduce_sums(sums, group)
+                n_tot = int(n_global) if n_global else B * HW * world
+                L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, n_tot, float(cw1), float(cw2), int(sup),
+                                               scalars.data_ptr(), L.stream_ptr()), "uaps_loss_finalize")
         ctx.save_for_backward(scalars, *([labels] if sup else []), *zs)
         ctx.meta = (K, B, C, HW, sup, flags, tuple(float(w) for w in mix_w) if not sup else None)
         extra = []
