@@ -207,20 +207,27 @@ def run_ours(args):
     zp, dzp, w_arr = L.ptr_array(z), L.ptr_array(dz), L.float_array(mix_w)
     st = L.stream_ptr()
 
+    xchg = None
+    if world > 1:                # the loss sums travel through NVLink peer mailboxes (NCCL only if that is unavailable)
+        from uaps_b200.comm import exchange_for
+        xchg = exchange_for(group, dev)
+
     def step(ev=None):
-        if ev: ev[0].record()
+        # ev = (after pass 1 + fold/finalize [+ all-reduce], after pass 2); the step starts where the previous one ended
         if world == 1:          # single rank: fold + finalize fused into one launch behind pass 1
             L.check(lib.uaps_loss_pass1_scalars(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0,
                                                 CW1, CW2, sc.data_ptr(), st), "pass1")
-            if ev: ev[1].record(); ev[2].record()
+        elif xchg is not None:  # fold + peer-memory exchange + finalize in one launch
+            L.check(lib.uaps_loss_pass1_exchange(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0,
+                                                 xchg.ptrs, rank, world, xchg.next_epoch(), N * world, CW1, CW2, sc.data_ptr(), st),
+                    "pass1")
         else:
             L.check(lib.uaps_loss_pass1(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0, st), "pass1")
-            if ev: ev[1].record()
             dist.all_reduce(sums, group=group)
             L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, N * world, CW1, CW2, 0, sc.data_ptr(), st), "finalize")
-            if ev: ev[2].record()
+        if ev: ev[0].record()
         L.check(lib.uaps_loss_pass2(zp, K, B, C, H * W, w_arr, None, sc.data_ptr(), go.data_ptr(), dzp, 0, st), "pass2")
-        if ev: ev[3].record()
+        if ev: ev[1].record()
 
     def barrier():
         if world > 1:
@@ -233,7 +240,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     # ---- timed region: device-resident inputs ---------------------------------------------------
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     barrier()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -242,9 +249,9 @@ def run_ours(args):
     t_end.record()
     barrier()
     ms_total = t_start.elapsed_time(t_end)
-    t1 = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    t2 = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
-    tmid = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    starts = [t_start] + [e[1] for e in evs[:-1]]
+    t1 = sum(s.elapsed_time(e[0]) for s, e in zip(starts, evs)) / args.steps      # pass 1 + fold/finalize (+ all-reduce)
+    t2 = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps                   # pass 2
 
     # ---- e2e: public API, pinned host logits -> H2D -> fwd + bwd -> D2H loss scalars ---------------
     zh = [torch.empty((B, C, H, W), dtype=torch.float32).pin_memory() for _ in range(K)]
@@ -276,10 +283,10 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks ------------------------------------------------------------------------
-    t = torch.tensor([ms_total, ms_e2e, t1, t2, tmid], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, t1, t2], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, t1, t2, tmid = t.tolist()
+    ms_total, ms_e2e, t1, t2 = t.tolist()
 
     # secondary shape (DAGM-sized images): same kernels, 4x the pixels per launch
     sweep = None
@@ -308,19 +315,21 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "K": K, "C": C, "H": H, "W": W, "batch_per_gpu": B,
                        "l2": "inputs (268 MB logits + 268 MB gradients per GPU) larger than the 126 MB L2; no flush",
-                       "parallelism": f"dp{world}" if world > 1 else "single"},
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "exchange": None if world == 1 else ("nvlink peer-memory mailboxes, fused into the fold kernel"
+                                                            if xchg is not None else "nccl all-reduce of the sums")},
             "roofline": {"bound": "hbm", "kernel": "loss_pass2_kernel<4,4,4>", "achieved": ach2, "peak": peak,
                          "unit": "GB/s", "frac": ach2 / peak, "peak_source": peak_src,
                          "traffic": None if not traffic else traffic.get("pass2_dram_bytes_per_launch"),
                          "algorithmic_bytes_per_launch": bytes2,
                          "fwd_bwd_frac": (bytes1 + bytes2) / (ms_step * 1e-3) / 1e9 / peak},
-            "kernels": {"pass1": {"ms": t1, "GBps": ach1, "frac": ach1 / peak, "algorithmic_bytes": bytes1},
-                        "pass2": {"ms": t2, "GBps": ach2, "frac": ach2 / peak, "algorithmic_bytes": bytes2},
-                        "finalize_plus_allreduce_ms": tmid},
+            "kernels": {"pass1_fold_finalize" + ("_exchange" if world > 1 else ""):
+                            {"ms": t1, "GBps": ach1, "frac": ach1 / peak, "algorithmic_bytes": bytes1},
+                        "pass2": {"ms": t2, "GBps": ach2, "frac": ach2 / peak, "algorithmic_bytes": bytes2}},
             "e2e": {"value": N * world * e2e_steps / (ms_e2e * 1e-3), "unit": "pixels/s",
                     "h2d_bytes_per_step": 4 * K * C * N, "d2h_bytes_per_step": 12, "steps": e2e_steps,
                     "api": "uaps_b200.losses.uaps_unlabeled_loss + backward, pinned host logits"},
-            "gpu_launches": (3 if world == 1 else 4) * args.steps,   # pass1, fold(+finalize), [finalize], pass2 per step
+            "gpu_launches": (3 if (world == 1 or xchg is not None) else 4) * args.steps,   # pass1, fold(+exchange)+finalize, pass2
             "clocks": clocks,
         }
         if world == 1:

@@ -106,6 +106,30 @@ int uaps_loss_pass1_scalars(const float* const* z, int K, int B, int C, int64_t 
                             int64_t* pseudo_out, float* const* exp_var_out, int flags,
                             float cw1, float cw2, float* scalars, cudaStream_t stream);
 
+/* ---- multi-GPU exchange (replaces the DataParallel gather of UAPS_model.py:13 for the loss sums) ----------
+ * One process per GPU, all on one NVLink/NVSwitch domain.  Each rank owns a MAILBOX (device memory allocated by
+ * uaps_xchg_alloc -- the one allocation this library makes, because CUDA IPC needs the allocation base) and maps
+ * every peer's mailbox through a 64-byte handle exchanged out of band (torch.distributed in uaps_b200/comm.py).
+ * uaps_loss_pass1_exchange = pass 1, then ONE kernel that folds the partial sums, stores them into every rank's
+ * mailbox over NVLink, waits for the world's sums and finalizes the scalars -- no NCCL call on the data path.
+ * mailboxes: host array of `world` device pointers as mapped in THIS process (own mailbox at [rank]);
+ * epoch: 1, 2, 3, ... incremented by the caller per exchange, identical on all ranks; N_global: pixels of the
+ * whole batch.  A peer that never arrives (UAPS_XCHG_TIMEOUT_MS, default 4000) turns the scalars into NaN and
+ * latches the epoch into the status word (uaps_xchg_status) instead of hanging the GPU. */
+#define UAPS_XCHG_MAX_RANKS 8
+size_t uaps_xchg_mailbox_bytes(void);
+int uaps_xchg_alloc(void** mailbox);
+int uaps_xchg_free(void* mailbox);
+int uaps_xchg_export(void* mailbox, void* handle64);
+int uaps_xchg_import(const void* handle64, void** peer_mailbox);
+int uaps_xchg_close(void* peer_mailbox);
+int uaps_xchg_status(const void* mailbox, unsigned* status_out, cudaStream_t stream);
+int uaps_loss_pass1_exchange(const float* const* z, int K, int B, int C, int64_t HW,
+                             const float* mix_w, const int64_t* labels, void* workspace, double* sums,
+                             int64_t* pseudo_out, float* const* exp_var_out, int flags,
+                             void* const* mailboxes, int rank, int world, unsigned epoch, int64_t N_global,
+                             float cw1, float cw2, float* scalars, cudaStream_t stream);
+
 /* sums_global: device, uaps_loss_sums_count doubles (all-reduced over ranks by the caller when
  * the batch is sharded); N_global = total pixels behind those sums.  supervised != 0 selects
  * the labeled-batch formula (scalars[LOSS_U] = mean_k 0.5(CE_k + Dice_k), cw ignored). */

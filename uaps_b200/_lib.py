@@ -30,6 +30,15 @@ _SIGNATURES = {
     "uaps_loss_workspace_bytes": (C.c_size_t, [_i, _i]),
     "uaps_loss_pass1": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "uaps_loss_pass1_scalars": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp]),
+    "uaps_loss_pass1_exchange": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, C.c_uint, _i64,
+                                      _f, _f, _vp, _vp]),
+    "uaps_xchg_mailbox_bytes": (C.c_size_t, []),
+    "uaps_xchg_alloc": (_i, [_vp]),
+    "uaps_xchg_free": (_i, [_vp]),
+    "uaps_xchg_export": (_i, [_vp, _vp]),
+    "uaps_xchg_import": (_i, [_vp, _vp]),
+    "uaps_xchg_close": (_i, [_vp]),
+    "uaps_xchg_status": (_i, [_vp, _vp, _vp]),
     "uaps_loss_finalize": (_i, [_vp, _i, _i, _i64, _f, _f, _i, _vp, _vp]),
     "uaps_loss_pass2": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "uaps_feature_noise": (_i, [_vp, _vp, _u64, _f, _vp, _i, _i64, _vp]),

@@ -1,0 +1,103 @@
+"""Peer-memory exchange for the loss sums: the host half of uaps_xchg_* / uaps_loss_pass1_exchange.
+
+One ``LossExchange`` per (process group, device): allocates this rank's mailbox, trades CUDA-IPC handles with
+the other ranks through ``torch.distributed`` (plumbing only -- no collective runs on the data path afterwards),
+maps every peer's mailbox and hands the fused kernel the pointer table plus a per-call epoch.  All ranks must
+call the loss functions in the same order (they do: one training loop per rank), which keeps the epochs equal.
+
+Used when every rank of the group sits on this node and UAPS_LOSS_EXCHANGE is not "nccl"; otherwise the loss
+falls back to fold -> ncclAllReduce -> finalize (still device code, but three launches and NCCL's latency).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import socket
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+MAX_RANKS = 8
+
+
+class LossExchange:
+    def __init__(self, group=None, device: Optional[torch.device] = None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > MAX_RANKS:
+            raise RuntimeError(f"the peer-memory exchange supports up to {MAX_RANKS} ranks, got {self.world}")
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = L.lib()
+        with torch.cuda.device(self.device):
+            own = C.c_void_p()
+            L.check(lib.uaps_xchg_alloc(C.byref(own)), "uaps_xchg_alloc")
+            self.own = own.value
+            handle = C.create_string_buffer(64)
+            L.check(lib.uaps_xchg_export(self.own, handle), "uaps_xchg_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.ptrs = (C.c_void_p * self.world)()
+            self._opened = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs[r] = self.own
+                else:
+                    p = C.c_void_p()
+                    L.check(lib.uaps_xchg_import(C.create_string_buffer(h, 64), C.byref(p)), "uaps_xchg_import")
+                    self.ptrs[r] = p.value
+                    self._opened.append(p.value)
+            dist.barrier(group=group)             # every mailbox is zeroed and mapped before the first store
+        self.epoch = 0
+
+    def next_epoch(self) -> int:
+        self.epoch = self.epoch % 0x7FFFFFFF + 1
+        return self.epoch
+
+    def status(self) -> int:
+        """0, or the epoch of the first exchange that timed out waiting for a peer (synchronises the stream)."""
+        out = C.c_uint(0)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().uaps_xchg_status(self.own, C.byref(out), L.stream_ptr()), "uaps_xchg_status")
+        return int(out.value)
+
+    def close(self) -> None:
+        lib = L.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in self._opened:
+                lib.uaps_xchg_close(p)
+            self._opened = []
+            if self.own:
+                lib.uaps_xchg_free(self.own)
+                self.own = None
+
+
+_exchanges: Dict[tuple, Optional[LossExchange]] = {}
+
+
+def exchange_for(group, device: torch.device) -> Optional[LossExchange]:
+    """The exchange of (group, device), created on first use; None when the group cannot use peer memory
+    (not NCCL, ranks on several hosts, more than 8 ranks, or UAPS_LOSS_EXCHANGE=nccl)."""
+    if not dist.is_initialized():
+        return None
+    key = (id(group) if group is not None else 0, device.index)
+    if key not in _exchanges:
+        ok = (os.environ.get("UAPS_LOSS_EXCHANGE", "peer") != "nccl" and dist.get_backend(group) == "nccl"
+              and 1 < dist.get_world_size(group) <= MAX_RANKS)
+        if ok:                                   # collective decision: every rank must take the same branch
+            hosts = [None] * dist.get_world_size(group)
+            dist.all_gather_object(hosts, socket.gethostname(), group=group)
+            ok = len(set(hosts)) == 1
+        _exchanges[key] = LossExchange(group, device) if ok else None
+    return _exchanges[key]
+
+
+def close_all() -> None:
+    for x in _exchanges.values():
+        if x is not None:
+            x.close()
+    _exchanges.clear()

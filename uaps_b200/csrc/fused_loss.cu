@@ -3,6 +3,7 @@
 // the vector width; it never allocates, synchronises or retains pointers.
 #define UAPS_LOSS_ENTRY
 #include <cstdlib>
+#include <cstring>
 #include "fused_loss_impl.cuh"
 
 namespace uaps {
@@ -68,6 +69,107 @@ int dispatch_k(int K, int C, int impl, bool sup, bool pass2, const LossArgs& a, 
     return UAPS_ERANGE;
 }
 
+
+// ---- multi-GPU: fold + exchange over NVLink peer memory + finalize, one launch ------------------------------
+// The path's single exchange step (the <= 70-double partial-sum vector between the passes) done by
+// the fold kernel itself instead of fold -> ncclAllReduce -> finalize: every rank stores its folded sums into
+// slot [rank] of EVERY rank's mailbox (P2P stores through NVLink/NVSwitch), raises a per-source flag, waits for
+// the world's flags in its own mailbox and adds the slots in rank order -- the same order on every rank, so all
+// ranks finalize bit-identical scalars.  Flags carry the call's epoch (no resets); two phases alternate so a
+// fast rank's next exchange never overwrites slots a slow rank is still reading (a rank can only be one
+// exchange ahead: it cannot leave exchange e+1 before every peer has entered it).
+constexpr int XCHG_WMAX = UAPS_XCHG_MAX_RANKS;
+constexpr int XCHG_SLOT = 128;                                  // doubles per (phase, source) slot, >= sums_count max
+constexpr size_t XCHG_FLAGS_OFF = (size_t)2 * XCHG_WMAX * XCHG_SLOT * sizeof(double);
+constexpr int XCHG_FLAG_STRIDE = 32;                            // one flag per 128-byte line
+constexpr size_t XCHG_STATUS_OFF = XCHG_FLAGS_OFF + (size_t)2 * XCHG_WMAX * XCHG_FLAG_STRIDE * sizeof(unsigned);
+constexpr size_t XCHG_BYTES = XCHG_STATUS_OFF + 128;
+static_assert(sums_count(KMAX, CMAX) <= XCHG_SLOT, "slot too small");
+
+struct ExchangeArgs {
+    char* box[XCHG_WMAX];        // mailbox of every rank as mapped into THIS process (own one at [rank])
+    int rank, world;
+    unsigned epoch;              // 1, 2, 3, ... identical on all ranks for one exchange
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const float* __restrict__ partials, int S, unsigned nblocks,
+                                                                            double* __restrict__ sums, const ExchangeArgs x, int K,
+                                                                            int C, double N, float cw1, float cw2, int supervised,
+                                                                            float* __restrict__ sc, int nsc) {
+    __shared__ double s_sums[XCHG_SLOT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < S; i += 32) {                         // local fold, as loss_fold_finalize_kernel
+        const float* row = partials + (size_t)i * LOSS_MAX_BLOCKS;
+        float v[LOSS_MAX_BLOCKS / kWarp];
+#pragma unroll
+        for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) {
+            const unsigned blk = u * kWarp + lane;
+            v[u] = (blk < nblocks) ? __ldcg(row + blk) : 0.f;
+        }
+        double r = 0.0;
+#pragma unroll
+        for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) r += (double)v[u];
+        r = warp_sum(r);
+        if (lane == 0) s_sums[i] = r;
+    }
+    __syncthreads();
+    const int ph = x.epoch & 1;
+    // scatter: my sums into slot [ph][rank] of every mailbox (peer stores travel over NVLink)
+    for (int t = threadIdx.x; t < x.world * S; t += blockDim.x) {
+        const int p = t / S, i = t - p * S;
+        double* dst = reinterpret_cast<double*>(x.box[p]) + ((size_t)(ph * XCHG_WMAX + x.rank) * XCHG_SLOT + i);
+        __stcg(dst, s_sums[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < x.world) {
+        unsigned* f = reinterpret_cast<unsigned*>(x.box[threadIdx.x] + XCHG_FLAGS_OFF) + (ph * XCHG_WMAX + x.rank) * XCHG_FLAG_STRIDE;
+        st_release_sys(f, x.epoch);
+    }
+    // gather: wait until every source's flag in MY mailbox reached this epoch (bounded spin: a dead peer must not
+    // hang the GPU -- on timeout the scalars become NaN and the status word records the epoch)
+    int timed_out = 0;
+    if (threadIdx.x < x.world) {
+        const unsigned* f = reinterpret_cast<const unsigned*>(x.box[x.rank] + XCHG_FLAGS_OFF) +
+                            (ph * XCHG_WMAX + threadIdx.x) * XCHG_FLAG_STRIDE;
+        const unsigned long long t0 = global_timer_ns();
+        while ((int)(ld_acquire_sys(f) - x.epoch) < 0) {
+            if (global_timer_ns() - t0 > x.timeout_ns) { timed_out = 1; break; }
+            __nanosleep(64);
+        }
+    }
+    timed_out = __syncthreads_or(timed_out);
+    if (timed_out) {
+        for (int i = threadIdx.x; i < nsc; i += blockDim.x) sc[i] = __int_as_float(0x7fc00000);
+        if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(x.box[x.rank] + XCHG_STATUS_OFF) = x.epoch;
+        return;
+    }
+    if (threadIdx.x < S) {
+        const double* mine = reinterpret_cast<const double*>(x.box[x.rank]) + (size_t)ph * XCHG_WMAX * XCHG_SLOT + threadIdx.x;
+        double r = 0.0;
+        for (int p = 0; p < x.world; ++p) r += __ldcg(mine + (size_t)p * XCHG_SLOT);     // rank order: identical on all ranks
+        s_sums[threadIdx.x] = r;
+        sums[threadIdx.x] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) finalize_from_sums(s_sums, K, C, N, cw1, cw2, supervised, sc);
+}
+
 }  // namespace
 }  // namespace uaps
 
@@ -90,7 +192,7 @@ UAPS_API size_t uaps_loss_workspace_bytes(int K, int C) {
 static int loss_pass1_impl(const float* const* z, int K, int B, int C, int64_t HW,
                                const float* mix_w, const int64_t* labels, void* workspace, double* sums,
                                int64_t* pseudo_out, float* const* exp_var_out, int flags, cudaStream_t stream,
-                          int64_t N_global, float cw1, float cw2, float* scalars) {
+                          int64_t N_global, float cw1, float cw2, float* scalars, const ExchangeArgs* xchg = nullptr) {
     int rc = check_common(z, K, B, C, HW, mix_w, labels);
     if (rc != UAPS_OK) return rc;
     if (workspace == nullptr || sums == nullptr) return UAPS_EINVAL;
@@ -113,7 +215,10 @@ static int loss_pass1_impl(const float* const* z, int K, int B, int C, int64_t H
     rc = dispatch_k(K, C, impl, labels != nullptr, false, a, partials, nullptr, nullptr, &nblocks, stream);
     if (rc != UAPS_OK) return rc;
     const int S = sums_count(K, C);
-    if (scalars != nullptr)
+    if (xchg != nullptr)
+        loss_fold_exchange_finalize_kernel<<<1, 1024, 0, stream>>>(partials, S, (unsigned)nblocks, sums, *xchg, K, C, (double)N_global,
+                                                                   cw1, cw2, labels != nullptr, scalars, scalars_count(K, C));
+    else if (scalars != nullptr)
         loss_fold_finalize_kernel<<<1, 1024, 0, stream>>>(partials, S, (unsigned)nblocks, sums, K, C, (double)N_global, cw1, cw2,
                                                           labels != nullptr, scalars);
     else
@@ -137,6 +242,62 @@ UAPS_API int uaps_loss_pass1_scalars(const float* const* z, int K, int B, int C,
     if (scalars == nullptr || !aligned_to(scalars, 4)) return UAPS_EINVAL;
     return loss_pass1_impl(z, K, B, C, HW, mix_w, labels, workspace, sums, pseudo_out, exp_var_out, flags, stream,
                            (int64_t)B * HW, cw1, cw2, scalars);
+}
+
+// ---- exchange mailboxes (multi-GPU, one process per GPU on one NVLink domain) ---------------------------------
+UAPS_API size_t uaps_xchg_mailbox_bytes(void) { return XCHG_BYTES; }
+
+UAPS_API int uaps_xchg_alloc(void** mailbox) {
+    if (mailbox == nullptr) return UAPS_EINVAL;
+    cudaError_t e = cudaMalloc(mailbox, XCHG_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(*mailbox, 0, XCHG_BYTES);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    return (int)e;
+}
+UAPS_API int uaps_xchg_free(void* mailbox) { return mailbox ? (int)cudaFree(mailbox) : UAPS_OK; }
+
+UAPS_API int uaps_xchg_export(void* mailbox, void* handle64) {
+    if (mailbox == nullptr || handle64 == nullptr) return UAPS_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    return (int)cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), mailbox);
+}
+UAPS_API int uaps_xchg_import(const void* handle64, void** peer_mailbox) {
+    if (handle64 == nullptr || peer_mailbox == nullptr) return UAPS_EINVAL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess);
+}
+UAPS_API int uaps_xchg_close(void* peer_mailbox) { return peer_mailbox ? (int)cudaIpcCloseMemHandle(peer_mailbox) : UAPS_OK; }
+
+UAPS_API int uaps_xchg_status(const void* mailbox, unsigned* status_out, cudaStream_t stream) {
+    if (mailbox == nullptr || status_out == nullptr) return UAPS_EINVAL;
+    cudaError_t e = cudaMemcpyAsync(status_out, reinterpret_cast<const char*>(mailbox) + XCHG_STATUS_OFF, sizeof(unsigned),
+                                    cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    return (int)e;
+}
+
+// pass 1 + fold + peer-memory exchange + finalize: the multi-rank counterpart of uaps_loss_pass1_scalars
+UAPS_API int uaps_loss_pass1_exchange(const float* const* z, int K, int B, int C, int64_t HW, const float* mix_w,
+                                      const int64_t* labels, void* workspace, double* sums, int64_t* pseudo_out,
+                                      float* const* exp_var_out, int flags, void* const* mailboxes, int rank, int world,
+                                      unsigned epoch, int64_t N_global, float cw1, float cw2, float* scalars,
+                                      cudaStream_t stream) {
+    if (scalars == nullptr || mailboxes == nullptr || N_global <= 0 || epoch == 0) return UAPS_EINVAL;
+    if (world < 1 || world > XCHG_WMAX || rank < 0 || rank >= world) return UAPS_ERANGE;
+    if (!aligned_to(scalars, 4)) return UAPS_EALIGN;
+    ExchangeArgs x{};
+    for (int p = 0; p < world; ++p) {
+        if (mailboxes[p] == nullptr) return UAPS_EINVAL;
+        if (!aligned_to(mailboxes[p], 128)) return UAPS_EALIGN;
+        x.box[p] = reinterpret_cast<char*>(mailboxes[p]);
+    }
+    x.rank = rank; x.world = world; x.epoch = epoch;
+    const char* tmo = getenv("UAPS_XCHG_TIMEOUT_MS");
+    x.timeout_ns = (tmo ? strtoull(tmo, nullptr, 10) : 4000ull) * 1000000ull;
+    return loss_pass1_impl(z, K, B, C, HW, mix_w, labels, workspace, sums, pseudo_out, exp_var_out, flags, stream, N_global, cw1,
+                           cw2, scalars, &x);
 }
 
 

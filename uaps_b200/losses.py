@@ -100,11 +100,19 @@ class _FusedLossFn(torch.autograd.Function):
                 L.check(lib.uaps_loss_pass1_scalars(*common, float(cw1), float(cw2), scalars.data_ptr(), L.stream_ptr()),
                         "uaps_loss_pass1_scalars")
             else:
-                L.check(lib.uaps_loss_pass1(*common, L.stream_ptr()), "uaps_loss_pass1")
-                world = _allreduce_sums(sums, group)
-                n_tot = int(n_global) if n_global else B * HW * world
-                L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, n_tot, float(cw1), float(cw2), int(sup),
-                                               scalars.data_ptr(), L.stream_ptr()), "uaps_loss_finalize")
+                from .comm import exchange_for
+                xchg = exchange_for(group, dev) if dist.is_initialized() else None
+                if xchg is not None:                 # fold + NVLink peer-memory exchange + finalize in one kernel
+                    n_tot = int(n_global) if n_global else B * HW * xchg.world
+                    L.check(lib.uaps_loss_pass1_exchange(*common, xchg.ptrs, xchg.rank, xchg.world, xchg.next_epoch(), n_tot,
+                                                         float(cw1), float(cw2), scalars.data_ptr(), L.stream_ptr()),
+                            "uaps_loss_pass1_exchange")
+                else:
+                    L.check(lib.uaps_loss_pass1(*common, L.stream_ptr()), "uaps_loss_pass1")
+                    world = _allreduce_sums(sums, group)
+                    n_tot = int(n_global) if n_global else B * HW * world
+                    L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, n_tot, float(cw1), float(cw2), int(sup),
+                                                   scalars.data_ptr(), L.stream_ptr()), "uaps_loss_finalize")
         ctx.save_for_backward(scalars, *([labels] if sup else []), *zs)
         ctx.meta = (K, B, C, HW, sup, flags, tuple(float(w) for w in mix_w) if not sup else None)
         extra = []
