@@ -211,6 +211,11 @@ int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, const void* 
 int uaps_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, int C, int backward, cudaStream_t stream);
 int uaps_maxpool2_nhwc(const void* x, const void* gy, void* out, int B, int H, int W, int C, cudaStream_t stream);
 
+/* [B,C,H,W] fp32 NCHW -> [B,H,W,Cp] bf16 channels-last, channels C..Cp-1 zero-filled (Cp % 8 == 0, Cp >= C): the
+ * entry into the bf16 path for the network input (UAPS_train.py:177,185 feed NCHW fp32 batches) and for the
+ * fp32 logits gradient coming back from the fused loss. */
+int uaps_nchw_f32_to_nhwc_bf16(const float* x, void* out, int B, int C, int H, int W, int Cp, cudaStream_t stream);
+
 /* Fused train-mode BatchNorm2d + LeakyReLU(slope) + Dropout(p) on channels-last bf16 activations
  * (utilities/UAPS_unet.py:37-43: nn.BatchNorm2d -> nn.LeakyReLU() -> nn.Dropout(p)).  y: [npix, C] bf16,
  * C a power of two in 8..256.  sum / sumsq: device fp64 [C], zeroed by the caller before _stats.

@@ -43,3 +43,25 @@ def test_maxpool2(B, C, H, W):
     (out.float() * cot.float()).sum().backward()
     assert torch.equal(out.float(), ref)
     assert torch.equal(xo.grad.float(), xr.grad)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 32), (3, 4, 48, 16), (1, 16, 8, 8), (2, 21, 16, 16)])
+def test_nchw_f32_to_nhwc_bf16(shape):
+    """Entry of the bf16 path: layout + dtype conversion with zero-filled padding channels, bit-exact vs torch."""
+    from uaps_b200.conv import pad16, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    x = torch.randn(*shape, device=dev)
+    out = to_nhwc_bf16(x)
+    B, C, H, W = shape
+    assert out.shape == (B, H, W, pad16(C)) and out.dtype == torch.bfloat16
+    assert torch.equal(out[..., :C], x.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert (out[..., C:] == 0).all()
+
+
+def test_channel_sums_match_torch():
+    from uaps_b200.conv import channel_sums
+    dev = torch.device("cuda:0")
+    g = torch.randn(4, 32, 24, 64, device=dev).to(torch.bfloat16)          # [B,H,W,C]
+    got = channel_sums(g, 50)
+    ref = g.double().sum(dim=(0, 1, 2))[:50]
+    torch.testing.assert_close(got.double(), ref, rtol=1e-6, atol=1e-4)

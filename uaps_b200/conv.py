@@ -20,11 +20,27 @@ def pad16(c: int) -> int:
 
 
 def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
-    """[B,C,H,W] float -> [B,H,W,pad16(C)] bf16 with zero padding channels."""
+    """[B,C,H,W] fp32 (NCHW) -> [B,H,W,pad16(C)] bf16 with zero padding channels, one kernel."""
+    L.require_cuda(x)
     B, C, H, W = x.shape
-    out = torch.zeros((B, H, W, pad16(C)), dtype=torch.bfloat16, device=x.device)
-    out[..., :C] = x.permute(0, 2, 3, 1)
+    x = x.float().contiguous()
+    out = torch.empty((B, H, W, pad16(C)), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().uaps_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), B, C, H, W, pad16(C), L.stream_ptr()),
+                "uaps_nchw_f32_to_nhwc_bf16")
     return out
+
+
+def channel_sums(x_nhwc: torch.Tensor, c: int) -> torch.Tensor:
+    """Per-channel sum over all pixels of a channels-last bf16 tensor (fp32 [c]): the bias gradient of a conv,
+    by the BatchNorm statistics kernel (fp64 accumulation)."""
+    npix, cp = x_nhwc.numel() // x_nhwc.shape[-1], x_nhwc.shape[-1]
+    sc = stepctx.current()
+    sums = sc.take(2 * cp) if sc is not None else torch.zeros(2 * cp, dtype=torch.float64, device=x_nhwc.device)
+    with torch.cuda.device(x_nhwc.device):
+        L.check(L.lib().uaps_bn_stats_nhwc(x_nhwc.data_ptr(), npix, cp, sums.data_ptr(), sums[cp:].data_ptr(), L.stream_ptr()),
+                "uaps_bn_stats_nhwc")
+    return sums[:c].float()
 
 
 def from_nhwc(y: torch.Tensor, c: int) -> torch.Tensor:
@@ -195,15 +211,16 @@ class _ConvFn(torch.autograd.Function):
     def backward(ctx, gy):
         x1, x2, weight = ctx.saved_tensors
         co, ci, ks, _ = weight.shape
-        if ctx.nchw:                                         # fp32 NCHW logits gradient -> bf16 channels_last
-            gy = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        elif not gy.is_contiguous(memory_format=torch.channels_last):
-            gy = gy.contiguous(memory_format=torch.channels_last)
-        gy_nhwc = gy.permute(0, 2, 3, 1)
-        if gy_nhwc.shape[-1] % 16:                            # pad the K segment to the kernel's granule
-            pad = torch.zeros((*gy_nhwc.shape[:3], pad16(co)), dtype=torch.bfloat16, device=gy.device)
-            pad[..., :co] = gy_nhwc
-            gy_nhwc = pad
+        if ctx.nchw:                                         # fp32 NCHW logits gradient -> bf16 channels-last, 16-padded
+            gy_nhwc = to_nhwc_bf16(gy)
+        else:
+            if not gy.is_contiguous(memory_format=torch.channels_last):
+                gy = gy.contiguous(memory_format=torch.channels_last)
+            gy_nhwc = gy.permute(0, 2, 3, 1)
+            if gy_nhwc.shape[-1] % 16:                        # pad the K segment to the kernel's granule
+                pad = torch.zeros((*gy_nhwc.shape[:3], pad16(co)), dtype=torch.bfloat16, device=gy.device)
+                pad[..., :co] = gy_nhwc
+                gy_nhwc = pad
         # data gradient: tcgen05 kernel, W'[ci][co] rotated by 180 degrees
         c1 = x1.shape[1]
         fold = pick_fold([co], ci if x2 is None else pad16(ci), ks, gy_nhwc.shape[2])
@@ -234,7 +251,7 @@ class _ConvFn(torch.autograd.Function):
             # a bias in front of train-mode BatchNorm has an analytically zero gradient; only conv1x1 /
             # out_conv (bias_grad=True) need the reduction
             if ctx.bias_grad:
-                gb = gy.float().sum(dim=(0, 2, 3))
+                gb = channel_sums(gy_nhwc, co)
             elif not direct:
                 gb = torch.zeros(co, dtype=torch.float32, device=gy.device)
         return g1, g2, gw, gb, None, None

@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from . import perturb as P
 from .bn_act import bn_lrelu_dropout
-from .conv import conv_bf16, pad16
+from .conv import conv_bf16, pad16, to_nhwc_bf16
 from .resample import maxpool2, upsample2x
 
 FT_CHNS = (16, 32, 64, 128, 256)            # UAPS_unet.py:212
@@ -129,8 +129,7 @@ class UNet_UAPS(nn.Module):
 
     def _encode16(self, x, enc_keep):
         B, C, H, W = x.shape
-        x16 = torch.zeros((B, pad16(C), H, W), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
-        x16[:, :C] = x
+        x16 = to_nhwc_bf16(x).permute(0, 3, 1, 2)             # logical NCHW, channels-last memory, 16-padded
         feats, cur = [], x16
         for lvl in range(5):
             if lvl == 0:
