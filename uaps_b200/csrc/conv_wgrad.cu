@@ -13,6 +13,7 @@
 // Putting Cout on N and the taps on M makes the tensor time 12 * Cout cycles per 128-pixel tile (192 for the
 // 16-channel layers) instead of 576+ with the roles swapped.  The 3 accumulators D_r (3 x Cout fp32 columns) stay
 // in TMEM across all pixel tiles of the CTA (split-K over CTAs), then are added to dW with fp32 reductions.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace uaps {
@@ -32,6 +33,7 @@ struct WgradArgs {
     int n_co;                                      // output channels per CTA (MMA N): multiple of 16, <= 128
     int two_boxes;                                 // cout > 64: second 64-channel box carries data
     float* dw;
+    int m_rows;                                    // MMA M: 64 when the taps x channel-chunk rows fit (halves the A-operand fetch), else 128
 };
 
 // MN-major descriptors (cute::UMMA canonical forms, units of 16 bytes):
@@ -43,8 +45,8 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t span, uint3
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
 // D = F32, A = B = BF16, both MN-major (bits 15, 16), N >> 3, M >> 4
-__device__ __forceinline__ uint32_t idesc_mn(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+__device__ __forceinline__ uint32_t idesc_mn(int n, int m) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -115,7 +117,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
                 // warps, each into its own accumulator: a single issuing thread, not the tensor pipe, was the
                 // limit (72 -> 24 -> 8 MMAs per issuing thread per pixel tile).
                 const int r = warp - 1;
-                const uint32_t idesc = idesc_mn(n_co);
+                const uint32_t idesc = idesc_mn(n_co, a.m_rows);
                 const uint32_t d = tmem_d + (uint32_t)(r * n_co);
                 for (int it = 0; it < ntiles; ++it) {
                     const int st = it % STAGES;
@@ -140,9 +142,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         // ---- epilogue: lane = (horizontal tap s, input channel ci); columns = output channels -> fp32 reductions into dW
         mbar_wait(&done_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = warp * 32 + lane;
+        // accumulator row -> TMEM lane: M=128 uses all 128 lanes in order; M=64 puts rows 16w..16w+15 in the first 16 lanes
+        // of warp w's lane quarter (cute::UMMA tmem_frg, "half subpartitions" atom)
+        const int row = a.m_rows == 64 ? warp * 16 + lane : warp * 32 + lane;
         const int s_tap = row / a.n_chunk, ci = a.ci_offset + nc * a.n_chunk + row % a.n_chunk;
-        const bool lane_ok = row < a.ks * a.n_chunk;
+        const bool lane_ok = row < a.ks * a.n_chunk && (a.m_rows == 128 || lane < 16);
         for (int r = 0; r < a.ks; ++r) {
             for (int j = 0; j < n_co / 16; ++j) {
                 float v[16];
@@ -219,6 +223,8 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     if (a.n_co != 16 && a.n_co != 32 && a.n_co != 64 && a.n_co != 128) return UAPS_ERANGE;   // 48/80/96/112: not a UNet_UAPS shape
     if (dy_c_stride < a.a_ch) return UAPS_ERANGE;                            // the dY box must lie inside the tensor's channels
     a.dw = dw;
+    static const bool no_m64 = getenv("UAPS_WGRAD_M128") != nullptr;           // A/B knob
+    a.m_rows = (ks * a.n_chunk <= 64 && !no_m64) ? 64 : 128;
     if (cin_pad != cin) return UAPS_ERANGE;                                  // callers pad Cin=3 layers on their side (see conv.py)
     const int n_chunks = cin_pad / a.n_chunk, m_tiles = (cout + 127) / 128;
     const int row_a = a.a_ch * 2, row_b = a.n_chunk * 2;
