@@ -34,6 +34,7 @@ struct WgradArgs {
     int two_boxes;                                 // cout > 64: second 64-channel box carries data
     float* dw;
     int m_rows;                                    // MMA M: 64 when the taps x channel-chunk rows fit (halves the A-operand fetch), else 128
+    int fused_r;                                   // 1: the vertical taps ride in N (dY box with a row halo), one MMA per k-step
 };
 
 // MN-major descriptors (cute::UMMA canonical forms, units of 16 bytes):
@@ -61,9 +62,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     const int box_w = TILE_W + halo;
     const int row_a = a.a_ch * 2;                                     // 32 / 64 / 128 bytes per pixel row of A
     const int row_b = a.n_chunk * 2;                                  // 32 or 64 bytes per pixel row of B
-    const int a_box = TILE_M * row_a;
+    // fused_r: the dY box carries the row halo ([16+2][8] pixels) and the X box only the column halo ([16][8+2])
+    const int a_box = (a.fused_r ? (TILE_H + halo) * TILE_W : TILE_M) * row_a;
     const int a_bytes = (a.two_boxes ? 2 : 1) * a_box;
-    const int b_bytes = (TILE_H + halo) * box_w * row_b;
+    const int b_bytes = (TILE_H + (a.fused_r ? 0 : halo)) * box_w * row_b;
+    const int n_issuers = a.fused_r ? 1 : a.ks;
     const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
     const int ntaps = a.ks * a.ks;
     // stride between the 128 / a_ch M groups: the second real box, or (fewer channels than M) one atom of the
@@ -81,8 +84,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 
     if (threadIdx.x == 0) {
         // the ks vertical taps are issued by ks different warps (warps 1..ks): each commits once per stage / at the end
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, a.ks); }
-        mbar_init(&done_bar, a.ks);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, n_issuers); }
+        mbar_init(&done_bar, n_issuers);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -103,13 +106,42 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
                     mbar_wait(empty_bar + st, ((it / STAGES) & 1) ^ 1);
                     unsigned char* sa = smem + (size_t)st * stage_bytes;
                     mbar_expect_tx(full_bar + st, a_bytes + b_bytes);
-                    tma_load_4d(sa, &map_dy, mt * 128, x0, y0, n_img, full_bar + st);
+                    const int ydy = a.fused_r ? y0 - halo / 2 : y0, yx = a.fused_r ? y0 : y0 - halo / 2;
+                    tma_load_4d(sa, &map_dy, mt * 128, x0, ydy, n_img, full_bar + st);
                     if (a.two_boxes) tma_load_4d(sa + a_box, &map_dy, mt * 128 + 64, x0, y0, n_img, full_bar + st);
-                    tma_load_4d(sa + a_bytes, &map_x, nc * a.n_chunk, x0 - halo / 2, y0 - halo / 2, n_img, full_bar + st);
+                    tma_load_4d(sa + a_bytes, &map_x, nc * a.n_chunk, x0 - halo / 2, yx, n_img, full_bar + st);
                 }
             }
             __syncwarp();
-        } else if (warp <= a.ks) {
+        } else if (warp == 1 && a.fused_r) {
+            if (lane == 0) {
+                // All nine taps in ONE instruction per 16-pixel k-step.  Substituting p' = p + (r-1, 0):
+                //   dW[r][s][ci][co] = sum_p' X[p' + (0, s-1)][ci] * dY[p' - (r-1, 0)][co]
+                // so with K = the tile's pixels p', M group s is the X tile shifted by s pixels (LBO = one pixel) and N
+                // group g = 2 - r is the dY tile shifted by g rows (LBO = one box row): N = 3 * Cout.  Versus one MMA per r
+                // this reads a third of the A operand (SS-mode operand fetch from shared memory is what bounds the
+                // small-channel layers, profiles/r01_conv_loader_experiments.txt).
+                const uint32_t idesc = idesc_mn(a.ks * n_co, a.m_rows);
+                for (int it = 0; it < ntiles; ++it) {
+                    const int st = it % STAGES;
+                    mbar_wait(full_bar + st, (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sdy = smem_u32(smem + (size_t)st * stage_bytes);
+                    const uint32_t sx = sdy + a_bytes;
+                    const uint64_t xd0 = desc_mn(sx, row_b, row_b, box_w * row_b);            // A: X, M groups one pixel apart
+                    const uint64_t yd0 = desc_mn(sdy, row_a, TILE_W * row_a, TILE_W * row_a);  // B: dY, N groups one row apart
+#pragma unroll
+                    for (int kk = 0; kk < TILE_M / 16; ++kk) {                    // 16 pixels (two image rows of the tile) per MMA
+                        const uint64_t xd = xd0 + (uint64_t)(((2 * kk * box_w) * row_b) >> 4);
+                        const uint64_t yd = yd0 + (uint64_t)((kk * 16 * row_a) >> 4);
+                        umma_bf16(tmem_d, xd, yd, idesc, (it | kk) != 0);
+                    }
+                    umma_commit(empty_bar + st);
+                }
+                umma_commit(&done_bar);
+            }
+            __syncwarp();
+        } else if (warp <= a.ks && !a.fused_r) {
             if (lane == 0) {
                 // The three horizontal taps of a row r are ONE instruction: the N-major B descriptor's group
                 // stride (LBO) is one pixel, so N group s is the same tile shifted by s pixels (N = 3 * n_chunk,
@@ -147,10 +179,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const int row = a.m_rows == 64 ? warp * 16 + lane : warp * 32 + lane;
         const int s_tap = row / a.n_chunk, ci = a.ci_offset + nc * a.n_chunk + row % a.n_chunk;
         const bool lane_ok = row < a.ks * a.n_chunk && (a.m_rows == 128 || lane < 16);
-        for (int r = 0; r < a.ks; ++r) {
+        for (int blk = 0; blk < a.ks; ++blk) {
+            // accumulator column block: per-r accumulators sit in order r; the fused layout's block g holds r = ks - 1 - g
+            const int r = a.fused_r ? a.ks - 1 - blk : blk;
             for (int j = 0; j < n_co / 16; ++j) {
                 float v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + r * n_co + j * 16, v);
+                tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + blk * n_co + j * 16, v);
                 if (lane_ok) {
                     const int co0 = mt * 128 + j * 16;
 #pragma unroll
@@ -225,10 +259,13 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     a.dw = dw;
     static const bool no_m64 = getenv("UAPS_WGRAD_M128") != nullptr;           // A/B knob
     a.m_rows = (ks * a.n_chunk <= 64 && !no_m64) ? 64 : 128;
+    static const bool no_fused = getenv("UAPS_WGRAD_PER_R") != nullptr;          // A/B knob
+    a.fused_r = (ks == 3 && !a.two_boxes && a.n_co == a.a_ch && !no_fused) ? 1 : 0;
     if (cin_pad != cin) return UAPS_ERANGE;                                  // callers pad Cin=3 layers on their side (see conv.py)
     const int n_chunks = cin_pad / a.n_chunk, m_tiles = (cout + 127) / 128;
     const int row_a = a.a_ch * 2, row_b = a.n_chunk * 2;
-    const int a_bytes = (a.two_boxes ? 2 : 1) * TILE_M * row_a, b_bytes = (TILE_H + ks - 1) * (TILE_W + ks - 1) * row_b;
+    const int dy_rows = TILE_H + (a.fused_r ? ks - 1 : 0), x_rows = TILE_H + (a.fused_r ? 0 : ks - 1);
+    const int a_bytes = (a.two_boxes ? 2 : 1) * dy_rows * TILE_W * row_a, b_bytes = x_rows * (TILE_W + ks - 1) * row_b;
     const size_t smem = (size_t)STAGES * ((a_bytes + b_bytes + 1023) & ~1023) + 1024;
     // split-K: enough CTAs to fill the machine (as many as fit per SM by shared memory and the 512 TMEM columns),
     // but at least 4 pixel tiles per CTA so the 9 * n_chunk * Cout reductions of the epilogue stay amortised
@@ -256,9 +293,9 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     a.tiles_per_cta = (a.tiles_total + splits - 1) / splits;
     splits = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
     CUtensorMap mdy, mx;
-    int rc = encode(&mdy, dy, B, H, W, dy_c_stride, a.a_ch, TILE_H, TILE_W);
+    int rc = encode(&mdy, dy, B, H, W, dy_c_stride, a.a_ch, dy_rows, TILE_W);
     if (rc != UAPS_OK) return rc;
-    rc = encode(&mx, x, B, H, W, x_c_stride, a.n_chunk, TILE_H + ks - 1, TILE_W + ks - 1);
+    rc = encode(&mx, x, B, H, W, x_c_stride, a.n_chunk, x_rows, TILE_W + ks - 1);
     if (rc != UAPS_OK) return rc;
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
