@@ -270,12 +270,20 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
                     bulk_g2s(smem + off, a.w_packed + off, min(16384, wbytes - off), &w_bar);
             }
             int itg = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-                const int nt = tile % a.n_tiles;
-                int t = tile / a.n_tiles;
-                const int tx = t % a.tiles_x; t /= a.tiles_x;
-                const int ty = t % a.tiles_y;
-                const int n_img = t / a.tiles_y;
+            // tile coordinates advance incrementally (see the epilogue): no div/mod per tile
+            int nt = blockIdx.x % a.n_tiles, tq = blockIdx.x / a.n_tiles;
+            int tx = tq % a.tiles_x; tq /= a.tiles_x;
+            int ty = tq % a.tiles_y;
+            int n_img = tq / a.tiles_y;
+            const int s_nt = gridDim.x % a.n_tiles;
+            int sq = gridDim.x / a.n_tiles;
+            const int s_tx = sq % a.tiles_x; sq /= a.tiles_x;
+            const int s_ty = sq % a.tiles_y;
+            const int s_n = sq / a.tiles_y;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x,
+                     nt += s_nt, tx += (nt >= a.n_tiles), nt -= (nt >= a.n_tiles) ? a.n_tiles : 0,
+                     tx += s_tx, ty += (tx >= a.tiles_x), tx -= (tx >= a.tiles_x) ? a.tiles_x : 0,
+                     ty += s_ty, n_img += (ty >= a.tiles_y), ty -= (ty >= a.tiles_y) ? a.tiles_y : 0, n_img += s_n) {
                 const int x0 = tx * TILE_W, y0 = ty * TILE_H;
                 const unsigned char* wsrc = a.w_packed + (size_t)nt * w_total;
                 int it = 0;
@@ -336,17 +344,31 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
         // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4 -------------------------------------------
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        const int ry = row / TILE_W, rx = row % TILE_W;
+        // The small-channel layers are instruction-issue bound (ncu: 315 instructions per epilogue warp per tile, a
+        // third of them three integer divisions), so the tile coordinates advance incrementally: mixed-radix step of
+        // tile = ((n_img * tiles_y + ty) * tiles_x + tx) * n_tiles + nt by gridDim.x
+        int nt = blockIdx.x % a.n_tiles, tq = blockIdx.x / a.n_tiles;
+        int tx = tq % a.tiles_x; tq /= a.tiles_x;
+        int ty = tq % a.tiles_y;
+        int n_img = tq / a.tiles_y;
+        const int s_nt = gridDim.x % a.n_tiles;
+        int sq = gridDim.x / a.n_tiles;
+        const int s_tx = sq % a.tiles_x; sq /= a.tiles_x;
+        const int s_ty = sq % a.tiles_y;
+        const int s_n = sq / a.tiles_y;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tcount) {
             const int buf = tcount & 1;
-            const int nt = tile % a.n_tiles;
-            int t = tile / a.n_tiles;
-            const int tx = t % a.tiles_x; t /= a.tiles_x;
-            const int ty = t % a.tiles_y;
-            const int n_img = t / a.tiles_y;
-            const int y = ty * TILE_H + row / TILE_W, x = tx * TILE_W + row % TILE_W;
+            const int y = ty * TILE_H + ry, x = tx * TILE_W + rx;
             const bool valid = (y < a.H) && (x < a.W);
             const int n0 = nt * a.n_tile;
+            const int n_cur = n_img;
+            // advance to this CTA's next tile
+            nt += s_nt; if (nt >= a.n_tiles) { nt -= a.n_tiles; ++tx; }
+            tx += s_tx; if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+            ty += s_ty; if (ty >= a.tiles_y) { ty -= a.tiles_y; ++n_img; }
+            n_img += s_n;
             mbar_wait(acc_full + buf, (tcount >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int j = 0; j < a.n_tile / 16; ++j) {
@@ -354,23 +376,33 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
                 tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + buf * a.n_tile + j * 16, v);
                 const int c0 = n0 + j * 16;
                 if (a.bias != nullptr) {
+                    if (c0 + 16 <= a.cout) {                       // whole group in range: four 16-byte loads
+                        const float4* b4 = reinterpret_cast<const float4*>(a.bias + c0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += (c0 + i < a.cout) ? __ldg(a.bias + c0 + i) : 0.f;
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = __ldg(b4 + i);
+                            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += (c0 + i < a.cout) ? __ldg(a.bias + c0 + i) : 0.f;
+                    }
                 }
                 if (!valid) continue;
                 if (a.out_nchw_f32) {
                     // logits: fp32 NCHW of the REAL image; a folded column block is (sub-pixel, channel)
-                    float* o = reinterpret_cast<float*>(a.out);
-                    const int sub = c0 / a.cpp, cb = c0 % a.cpp;
+                    const int sub = a.fold == 1 ? 0 : c0 / a.cpp, cb = a.fold == 1 ? c0 : c0 % a.cpp;
                     const int xr = x * a.fold + sub, Wr = a.W * a.fold;
+                    const size_t plane = (size_t)a.H * Wr;
+                    float* o = reinterpret_cast<float*>(a.out) + ((size_t)n_cur * a.cout_real + cb) * plane + (size_t)y * Wr + xr;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (cb + i < a.cout_real) o[(((size_t)n_img * a.cout_real + cb + i) * a.H + y) * Wr + xr] = v[i];
+                        if (cb + i < a.cout_real) o[(size_t)i * plane] = v[i];
                 } else {
-                    const size_t pix = ((size_t)n_img * a.H + y) * a.W + x;
+                    const size_t pix = ((size_t)n_cur * a.H + y) * a.W + x;
                     __nv_bfloat16* o;
                     if (a.out2 != nullptr) {                       // concat data gradient: per real pixel, channels [0,split) | [split,cpp)
-                        const int sub = c0 / a.cpp, cb = c0 % a.cpp, rest = a.cpp - a.split;
+                        const int sub = a.fold == 1 ? 0 : c0 / a.cpp, cb = a.fold == 1 ? c0 : c0 % a.cpp, rest = a.cpp - a.split;
                         o = cb < a.split
                             ? reinterpret_cast<__nv_bfloat16*>(a.out) + pix * (size_t)(a.fold * a.split) + sub * a.split + cb
                             : reinterpret_cast<__nv_bfloat16*>(a.out2) + pix * (size_t)(a.fold * rest) + sub * rest + (cb - a.split);
@@ -583,7 +615,9 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
     // the activation tensors must physically hold the zero-padded channel count (c*_stride), 16-byte aligned rows
     if (c1_stride < pl.seg_pad[0] || (c1_stride % 8) != 0 || (cin2 > 0 && (c2_stride < pl.seg_pad[1] || (c2_stride % 8) != 0)))
         return UAPS_ERANGE;
-    if (!aligned_to(x1, 16) || (x2 && !aligned_to(x2, 16)) || !aligned_to(out, 16) || !aligned_to(w_packed, 16)) return UAPS_EALIGN;
+    if (!aligned_to(x1, 16) || (x2 && !aligned_to(x2, 16)) || !aligned_to(out, 16) || !aligned_to(w_packed, 16) ||
+        (bias && !aligned_to(bias, 16)))
+        return UAPS_EALIGN;
     if (!out_nchw_f32 && (out_c_stride < (out2 != nullptr ? split : cout) || (out_c_stride % 8) != 0)) return UAPS_ERANGE;
     if (out2 != nullptr && out2_c_stride < cpp - split) return UAPS_ERANGE;
 
