@@ -419,7 +419,7 @@ def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3, c
     return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "images_per_s": 2 * batch * world * 1e3 / ms, "unit": "iters/s",
             "loss": float(loss_h), "config": f"UNet_UAPS 3x{H}x{W} C={C} K={K}, {batch}+{batch} images/GPU, "
             f"dp{world}, host images in the timed region (e2e)",
-            "convs": "tcgen05 implicit GEMM (fprop + dgrad), bf16 channels-last; wgrad/BN/pool/upsample via torch"
+            "kernels": "bf16 channels-last: tcgen05 implicit-GEMM fprop/dgrad/wgrad, fused BN+LeakyReLU+dropout, pool/upsample, Philox perturbations, fused losses (all hand-written sm_100a); torch: autograd glue, fused Adam"
             if compute == "bf16" else "cuDNN fp32 (reference-precision path)"}
 
 
