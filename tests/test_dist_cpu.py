@@ -78,6 +78,9 @@ def _worker(rank, world, port, ret):
         buf.all_reduce_sum(dist.group.WORLD)
         ok_grad = all(torch.all(p.grad == sum(range(1, world + 1))).item() for p in lin.parameters())
         ok_view = lin.weight.grad.data_ptr() == buf.flat.data_ptr()
+        # a gloo group can never use the NVLink peer mailboxes: the loss must pick the all-reduce route on every rank
+        from uaps_b200.comm import exchange_for
+        ok_view = ok_view and exchange_for(dist.group.WORLD, torch.device("cuda", 0)) is None
         ret[rank] = (loss.item(), ps.item(), unc.item(), ok_grad, ok_view)
     finally:
         dist.destroy_process_group()

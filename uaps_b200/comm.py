@@ -32,25 +32,34 @@ class LossExchange:
             raise RuntimeError(f"the peer-memory exchange supports up to {MAX_RANKS} ranks, got {self.world}")
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         lib = L.lib()
+        self.own, self._opened, self.ptrs = None, [], (C.c_void_p * self.world)()
+        # Every rank runs every collective below whatever happens locally (a rank that bailed out early would hang
+        # the others); failures are carried as None / flags and raised together at the end.
         with torch.cuda.device(self.device):
+            mine = None
             own = C.c_void_p()
-            L.check(lib.uaps_xchg_alloc(C.byref(own)), "uaps_xchg_alloc")
-            self.own = own.value
-            handle = C.create_string_buffer(64)
-            L.check(lib.uaps_xchg_export(self.own, handle), "uaps_xchg_export")
+            if lib.uaps_xchg_alloc(C.byref(own)) == 0:
+                self.own = own.value
+                handle = C.create_string_buffer(64)
+                if lib.uaps_xchg_export(self.own, handle) == 0:
+                    mine = bytes(handle.raw)
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self.ptrs = (C.c_void_p * self.world)()
-            self._opened = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.ptrs[r] = self.own
-                else:
+            dist.all_gather_object(handles, mine, group=group)
+            failed = any(h is None for h in handles)
+            if not failed:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self.ptrs[r] = self.own
+                        continue
                     p = C.c_void_p()
-                    L.check(lib.uaps_xchg_import(C.create_string_buffer(h, 64), C.byref(p)), "uaps_xchg_import")
+                    if lib.uaps_xchg_import(C.create_string_buffer(h, 64), C.byref(p)) != 0:
+                        failed = True
+                        break
                     self.ptrs[r] = p.value
                     self._opened.append(p.value)
-            dist.barrier(group=group)             # every mailbox is zeroed and mapped before the first store
+        if failed:
+            self.close()
+            raise RuntimeError("could not allocate / export / map the exchange mailboxes (CUDA IPC or peer access unavailable)")
         self.epoch = 0
 
     def next_epoch(self) -> int:
@@ -68,7 +77,7 @@ class LossExchange:
         lib = L.lib()
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
-            for p in self._opened:
+            for p in getattr(self, "_opened", []):
                 lib.uaps_xchg_close(p)
             self._opened = []
             if self.own:
@@ -92,7 +101,26 @@ def exchange_for(group, device: torch.device) -> Optional[LossExchange]:
             hosts = [None] * dist.get_world_size(group)
             dist.all_gather_object(hosts, socket.gethostname(), group=group)
             ok = len(set(hosts)) == 1
-        _exchanges[key] = LossExchange(group, device) if ok else None
+        xchg = None
+        if ok:
+            # mapping a peer's mailbox can fail (no P2P path, IPC disabled in the container ...): every rank must then
+            # take the NCCL route, so the outcome is agreed on collectively before anybody uses the exchange
+            err = None
+            try:
+                xchg = LossExchange(group, device)
+            except Exception as e:                 # noqa: BLE001 -- reported below, then the NCCL fallback is used
+                err = repr(e)
+            outcomes = [None] * dist.get_world_size(group)
+            dist.all_gather_object(outcomes, err, group=group)     # also the barrier: every mailbox zeroed and mapped
+            if any(o is not None for o in outcomes):
+                if xchg is not None:
+                    xchg.close()
+                xchg = None
+                if dist.get_rank(group) == 0:
+                    import warnings
+                    warnings.warn("uaps_b200: peer-memory exchange unavailable, using the NCCL all-reduce for the loss sums: "
+                                  + "; ".join(o for o in outcomes if o is not None)[:300])
+        _exchanges[key] = xchg
     return _exchanges[key]
 
 

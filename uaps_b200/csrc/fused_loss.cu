@@ -266,7 +266,9 @@ UAPS_API int uaps_xchg_import(const void* handle64, void** peer_mailbox) {
     if (handle64 == nullptr || peer_mailbox == nullptr) return UAPS_EINVAL;
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, sizeof(h));
-    return (int)cudaIpcOpenMemHandle(peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess);
+    const cudaError_t e = cudaIpcOpenMemHandle(peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) (void)cudaGetLastError();          // not sticky: the caller falls back to NCCL
+    return (int)e;
 }
 UAPS_API int uaps_xchg_close(void* peer_mailbox) { return peer_mailbox ? (int)cudaIpcCloseMemHandle(peer_mailbox) : UAPS_OK; }
 
