@@ -273,7 +273,8 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     while (tmem_cols < ks * a.n_co) tmem_cols <<= 1;
     int per_sm = (int)((227 * 1024) / (smem + 2048));
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
-    if (per_sm > 4) per_sm = 4;
+    static const int cap_env = [] { const char* e = getenv("UAPS_WGRAD_CTAS_PER_SM"); return e ? atoi(e) : 4; }();   // 6 measured slower
+    if (per_sm > cap_env) per_sm = cap_env;
     if (per_sm < 1) per_sm = 1;
     // split-K factor: trade main-loop length against the fp32 reductions of the epilogue (every split adds
     // cout * cin * taps of them; measured ~125 reductions/ns chip-wide) -- evaluate a simple cost model
