@@ -289,7 +289,7 @@ UAPS_API int uaps_bn_act_nhwc(const void* y, const double* sum, const double* su
     p.sum = sum; p.sumsq = sumsq; p.gamma = gamma; p.beta = beta; p.running_mean = running_mean; p.running_var = running_var;
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.momentum = momentum; p.eps = eps; p.slope = slope; p.p = (float)p_drop;
     p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
-    bn_act_kernel<<<bn_grid(npix * (C / 8)), BT, 0, stream>>>(reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(out), p);
+    bn_act_kernel<<<bn_grid(npix * (C / 8), 4), BT, 0, stream>>>(reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(out), p);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -309,9 +309,9 @@ UAPS_API int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float*
     p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
     if ((dgamma_accum == nullptr) != (dbeta_accum == nullptr)) return UAPS_EINVAL;
     p.dgamma_accum = dgamma_accum; p.dbeta_accum = dbeta_accum;
-    const int grid = bn_grid(npix * (C / 8));
+    const int grid = bn_grid(npix * (C / 8), 2);       // ~124 registers: 2 resident CTAs/SM = one persistent wave
     // sum_g / sum_gx (zeroed by the caller) receive sum(g') and sum(g' * xhat) = d beta and d gamma
-    bn_act_bwd_reduce_kernel<<<bn_grid(npix * (C / 8), 4), BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y), p,
+    bn_act_bwd_reduce_kernel<<<bn_grid(npix * (C / 8), 2), BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y), p,
                                                      sum_g, sum_gx);
     UAPS_LAUNCH_CHECK();
     bn_act_bwd_kernel<<<grid, BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y),
