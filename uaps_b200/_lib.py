@@ -94,6 +94,25 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed: {msg} (code {rc})")
 
 
+class _NoSwitch:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def on_device(dev: torch.device):
+    """Context that makes `dev` the current CUDA device -- a no-op object when it already is (one process per GPU:
+    always), which saves the cudaGetDevice/cudaSetDevice pair of torch.cuda.device on ~1200 calls per iteration."""
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(dev)
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -25,7 +25,7 @@ class _BnActFn(torch.autograd.Function):
         out = torch.empty_like(y)
         lib = L.lib()
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        with torch.cuda.device(dev):
+        with L.on_device(dev):
             L.check(lib.uaps_bn_stats_nhwc(y.data_ptr(), npix, C, sums.data_ptr(), sums[C:].data_ptr(), L.stream_ptr()),
                     "uaps_bn_stats_nhwc")
             L.check(lib.uaps_bn_act_nhwc(y.data_ptr(), sums.data_ptr(), sums[C:].data_ptr(), g32.data_ptr(), b32.data_ptr(),
@@ -52,7 +52,7 @@ class _BnActFn(torch.autograd.Function):
         gamma, beta = ctx.params
         direct = (sc is not None and sc.direct_grads and gamma.grad is not None and beta.grad is not None
                   and gamma.grad.dtype == torch.float32 and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
-        with torch.cuda.device(y.device):
+        with L.on_device(y.device):
             L.check(L.lib().uaps_bn_act_bwd_nhwc(g.data_ptr(), y.data_ptr(), g32.data_ptr(), b32.data_ptr(), stats.data_ptr(),
                                                  stats[C:].data_ptr(), slope, p_drop, seed, sums.data_ptr(),
                                                  sums[C:].data_ptr(), dy.data_ptr(),

@@ -25,7 +25,7 @@ def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     B, C, H, W = x.shape
     x = x.float().contiguous()
     out = torch.empty((B, H, W, pad16(C)), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
+    with L.on_device(x.device):
         L.check(L.lib().uaps_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), B, C, H, W, pad16(C), L.stream_ptr()),
                 "uaps_nchw_f32_to_nhwc_bf16")
     return out
@@ -37,7 +37,7 @@ def channel_sums(x_nhwc: torch.Tensor, c: int) -> torch.Tensor:
     npix, cp = x_nhwc.numel() // x_nhwc.shape[-1], x_nhwc.shape[-1]
     sc = stepctx.current()
     sums = sc.take(2 * cp) if sc is not None else torch.zeros(2 * cp, dtype=torch.float64, device=x_nhwc.device)
-    with torch.cuda.device(x_nhwc.device):
+    with L.on_device(x_nhwc.device):
         L.check(L.lib().uaps_bn_stats_nhwc(x_nhwc.data_ptr(), npix, cp, sums.data_ptr(), sums[cp:].data_ptr(), L.stream_ptr()),
                 "uaps_bn_stats_nhwc")
     return sums[:c].float()
@@ -89,7 +89,7 @@ class PackedConv:
         if nbytes == 0:
             raise RuntimeError("unsupported convolution shape")
         self.packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-        with torch.cuda.device(w.device):
+        with L.on_device(w.device):
             L.check(L.lib().uaps_conv_pack_weights(w.data_ptr(), self.packed.data_ptr(), self.cout, self.cin1, self.cin2,
                                                    ks, int(transpose), fold, L.stream_ptr()), "uaps_conv_pack_weights")
         self.bias = None if bias is None else bias.detach().float().contiguous()
@@ -117,7 +117,7 @@ class PackedConv:
             alloc = torch.zeros if (ocs != self.cout and not split and self.fold == 1) else torch.empty
             out = alloc((B, H, W, ocs), dtype=torch.bfloat16, device=x1.device)
         out2 = torch.empty((B, H, W, pad16(self.cout) - split), dtype=torch.bfloat16, device=x1.device) if split else None
-        with torch.cuda.device(x1.device):
+        with L.on_device(x1.device):
             L.check(L.lib().uaps_conv_fprop(x1.data_ptr(), c1s, None if x2 is None else x2.data_ptr(), c2s,
                                             self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(),
                                             out.data_ptr(), ocs, int(out_nchw_f32), B, H, W, self.cin1, self.cin2,
@@ -134,7 +134,7 @@ def conv_wgrad(dy_nhwc: torch.Tensor, xs, cout: int, cin_total: int, ks: int, ou
     B, H, W, dcs = dy_nhwc.shape
     dw = out if out is not None else torch.zeros((cout, cin_total, ks, ks), dtype=torch.float32, device=dy_nhwc.device)
     off = 0
-    with torch.cuda.device(dy_nhwc.device):
+    with L.on_device(dy_nhwc.device):
         for x in xs:
             c = x.shape[3]
             L.check(L.lib().uaps_conv_wgrad(dy_nhwc.data_ptr(), dcs, x.data_ptr(), c, dw.data_ptr(), B, H, W, cout, c,

@@ -83,7 +83,7 @@ class _FusedLossFn(torch.autograd.Function):
             if mix_w is None or len(mix_w) != K:
                 raise RuntimeError("mix_w must hold one weight per decoder")
             w_arr = L.float_array(mix_w)            # fp32 rounding = torch's python-scalar * tensor rule
-        with torch.cuda.device(dev):
+        with L.on_device(dev):
             sums = torch.empty(lib.uaps_loss_sums_count(K, C), dtype=torch.float64, device=dev)
             scalars = torch.empty(lib.uaps_loss_scalars_count(K, C), dtype=torch.float32, device=dev)
             pseudo = torch.empty((B, H, W), dtype=torch.int64, device=dev) if (want_pseudo and not sup) else None
@@ -134,7 +134,7 @@ class _FusedLossFn(torch.autograd.Function):
         dev = scalars.device
         # the autograd gradient of the scalars vector IS the kernel's grad_out (same layout)
         grad_out = g_scalars.to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with L.on_device(dev):
             dz = [torch.empty_like(z) for z in zs]
             L.check(L.lib().uaps_loss_pass2(L.ptr_array(zs), K, B, C, HW,
                                             None if sup else L.float_array(mix_w),

@@ -20,7 +20,7 @@ def confusion(logits: torch.Tensor, mask: torch.Tensor, out: torch.Tensor = None
     B, C, H, W = logits.shape
     logits, mask = logits.contiguous(), mask.reshape(B, H, W).long().contiguous()
     conf = out if out is not None else torch.zeros((C, C), dtype=torch.int64, device=logits.device)
-    with torch.cuda.device(logits.device):
+    with L.on_device(logits.device):
         L.check(L.lib().uaps_confusion(logits.data_ptr(), mask.data_ptr(), B, C, H * W, conf.data_ptr(), L.stream_ptr()),
                 "uaps_confusion")
     return conf

@@ -50,7 +50,7 @@ class _NoiseFn(torch.autograd.Function):
             if noise.numel() != chw:
                 raise RuntimeError("noise must have shape x.shape[1:]")
         ctx.noise, ctx.seed, ctx.rng = noise, seed, rng
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(L.lib().uaps_feature_noise(x.data_ptr(), None if noise is None else noise.data_ptr(), seed, rng,
                                                y.data_ptr(), B, chw, L.stream_ptr()), "uaps_feature_noise")
         return y
@@ -60,7 +60,7 @@ class _NoiseFn(torch.autograd.Function):
         g = g.contiguous()
         dx = torch.empty_like(g)
         B, chw = g.shape[0], g[0].numel()
-        with torch.cuda.device(g.device):
+        with L.on_device(g.device):
             L.check(L.lib().uaps_feature_noise(g.data_ptr(), None if ctx.noise is None else ctx.noise.data_ptr(),
                                                ctx.seed, ctx.rng, dx.data_ptr(), B, chw, L.stream_ptr()),
                     "uaps_feature_noise(bwd)")
@@ -90,7 +90,7 @@ class _DropoutFn(torch.autograd.Function):
             if keep.numel() != x.numel():
                 raise RuntimeError("keep mask must have x's shape")
         ctx.keep, ctx.seed, ctx.p = keep, seed, p
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(L.lib().uaps_dropout(x.data_ptr(), None if keep is None else keep.data_ptr(), seed, p,
                                          y.data_ptr(), x.numel(), L.stream_ptr()), "uaps_dropout")
         return y
@@ -99,7 +99,7 @@ class _DropoutFn(torch.autograd.Function):
     def backward(ctx, g):
         g = g.contiguous()
         dx = torch.empty_like(g)
-        with torch.cuda.device(g.device):
+        with L.on_device(g.device):
             L.check(L.lib().uaps_dropout(g.data_ptr(), None if ctx.keep is None else ctx.keep.data_ptr(), ctx.seed,
                                          ctx.p, dx.data_ptr(), g.numel(), L.stream_ptr()), "uaps_dropout(bwd)")
         return dx, None, None, None
@@ -118,7 +118,7 @@ def _fdrop_stats(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     B, C, H, W = x.shape
     attention = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
     smax = torch.zeros(B, dtype=torch.int32, device=x.device)
-    with torch.cuda.device(x.device):
+    with L.on_device(x.device):
         L.check(L.lib().uaps_fdrop_stats(x.data_ptr(), B, C, H * W, attention.data_ptr(), smax.data_ptr(),
                                          L.stream_ptr()), "uaps_fdrop_stats")
     return attention, smax
@@ -131,7 +131,7 @@ class _FeatureDropoutFn(torch.autograd.Function):
         B, C, H, W = x.shape
         attention, smax = _fdrop_stats(x)
         y = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(L.lib().uaps_fdrop_apply(x.data_ptr(), attention.data_ptr(), smax.data_ptr(), u, y.data_ptr(),
                                              B, C, H * W, L.stream_ptr()), "uaps_fdrop_apply")
         ctx.save_for_backward(attention, smax)
@@ -144,7 +144,7 @@ class _FeatureDropoutFn(torch.autograd.Function):
         g = g.contiguous()
         B, C, H, W = g.shape
         dx = torch.empty_like(g)
-        with torch.cuda.device(g.device):
+        with L.on_device(g.device):
             L.check(L.lib().uaps_fdrop_apply(g.data_ptr(), attention.data_ptr(), smax.data_ptr(), ctx.u, dx.data_ptr(),
                                              B, C, H * W, L.stream_ptr()), "uaps_fdrop_apply(bwd)")
         return dx, None
@@ -169,7 +169,7 @@ class _Perturb3Fn(torch.autograd.Function):
             keep = keep.to(device=x.device).to(torch.uint8).contiguous()
         attention, smax = _fdrop_stats(x)
         ys = [torch.empty_like(x) for _ in range(3)]
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(L.lib().uaps_perturb3(x.data_ptr(), None if noise is None else noise.data_ptr(),
                                           None if keep is None else keep.data_ptr(), seed, rng, p,
                                           attention.data_ptr(), smax.data_ptr(), u,
@@ -187,7 +187,7 @@ class _Perturb3Fn(torch.autograd.Function):
         ref = next(g for g in gs if g is not None)
         B, C, H, W = ref.shape
         dx = torch.empty_like(ref)
-        with torch.cuda.device(ref.device):
+        with L.on_device(ref.device):
             L.check(L.lib().uaps_perturb3_bwd(*[None if g is None else g.data_ptr() for g in gs],
                                               None if noise is None else noise.data_ptr(),
                                               None if keep is None else keep.data_ptr(), seed, rng, p,
@@ -218,7 +218,7 @@ class _Perturb3NhwcFn(torch.autograd.Function):
         smax = torch.zeros(B, dtype=torch.int32, device=x.device)
         ys = [torch.empty_like(x) for _ in range(3)]               # empty_like keeps channels_last
         lib = L.lib()
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(lib.uaps_fdrop_stats_nhwc(x.data_ptr(), B, C, H * W, attention.data_ptr(), smax.data_ptr(),
                                               L.stream_ptr()), "uaps_fdrop_stats_nhwc")
             L.check(lib.uaps_perturb3_nhwc(x.data_ptr(), seed, rng, p, attention.data_ptr(), smax.data_ptr(), u,
@@ -236,7 +236,7 @@ class _Perturb3NhwcFn(torch.autograd.Function):
         ref = next(g for g in gs if g is not None)
         B, C, H, W = ref.shape
         dx = torch.empty_like(ref)
-        with torch.cuda.device(ref.device):
+        with L.on_device(ref.device):
             L.check(L.lib().uaps_perturb3_nhwc_bwd(*[None if g is None else g.data_ptr() for g in gs], seed, rng, p,
                                                    attention.data_ptr(), smax.data_ptr(), u, dx.data_ptr(), B, C, H * W,
                                                    L.stream_ptr()), "uaps_perturb3_nhwc_bwd")

@@ -24,7 +24,7 @@ class _Upsample2xFn(torch.autograd.Function):
         _check_cl(x)
         B, C, H, W = x.shape
         y = _empty_cl(B, C, 2 * H, 2 * W, x.device)
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(L.lib().uaps_upsample2x_nhwc(x.data_ptr(), y.data_ptr(), B, H, W, C, 0, L.stream_ptr()), "uaps_upsample2x_nhwc")
         ctx.shape = (B, C, H, W)
         return y
@@ -34,7 +34,7 @@ class _Upsample2xFn(torch.autograd.Function):
         B, C, H, W = ctx.shape
         g = g.contiguous(memory_format=torch.channels_last)
         gx = _empty_cl(B, C, H, W, g.device)
-        with torch.cuda.device(g.device):
+        with L.on_device(g.device):
             L.check(L.lib().uaps_upsample2x_nhwc(g.data_ptr(), gx.data_ptr(), B, H, W, C, 1, L.stream_ptr()),
                     "uaps_upsample2x_nhwc(bwd)")
         return gx
@@ -46,7 +46,7 @@ class _MaxPool2Fn(torch.autograd.Function):
         _check_cl(x)
         B, C, H, W = x.shape
         y = _empty_cl(B, C, H // 2, W // 2, x.device)
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(L.lib().uaps_maxpool2_nhwc(x.data_ptr(), None, y.data_ptr(), B, H, W, C, L.stream_ptr()), "uaps_maxpool2_nhwc")
         ctx.save_for_backward(x)
         return y
@@ -57,7 +57,7 @@ class _MaxPool2Fn(torch.autograd.Function):
         B, C, H, W = x.shape
         g = g.contiguous(memory_format=torch.channels_last)
         gx = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with L.on_device(x.device):
             L.check(L.lib().uaps_maxpool2_nhwc(x.data_ptr(), g.data_ptr(), gx.data_ptr(), B, H, W, C, L.stream_ptr()),
                     "uaps_maxpool2_nhwc(bwd)")
         return gx
