@@ -102,6 +102,36 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def eager_cuda_baseline(dev, steps: int = 5, warmup: int = 2):
+    """BASELINE.md section 2, "also reported": the reference's own loss expressions (the oracle restatement, bit-identical
+    to the executed reference lines) as torch-eager ops ON THE SAME B200, same workload as the headline, fwd + bwd.
+    The incumbent GPU number the fused kernels replace -- a baseline leg, never part of the product path."""
+    from oracle.uaps_loss_ref import unlabeled_loss_ref
+    gen = torch.Generator(device=dev).manual_seed(1337)
+    z = [(torch.randn(B, C, H, W, generator=gen, device=dev) * 2).requires_grad_(True) for _ in range(K)]
+    mix_w = np.random.default_rng(1337).dirichlet(np.ones(K))
+
+    def one():
+        for t in z:
+            t.grad = None
+        unlabeled_loss_ref(z, mix_w, CW1, CW2)["loss_u"].backward()
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del z
+    torch.cuda.empty_cache()
+    return {"value": B * H * W / (ms * 1e-3), "unit": "pixels/s", "ms_per_step": ms,
+            "what": "reference expressions (UAPS_train.py:186-189, 223-282) as torch-eager CUDA ops on this GPU, fwd+bwd, same workload"}
+
+
 def cpu_baseline(steps: int, warmup: int, threads: int):
     """The oracle's unlabeled loss fwd+bwd on CPU torch (the reference's expressions), pixels/s."""
     from oracle.uaps_loss_ref import unlabeled_loss_ref
@@ -337,10 +367,19 @@ def run_ours(args):
             pxs, sec = cpu_baseline(5, 1, threads)
             line["cpu_baseline"] = {"value": pxs, "unit": "pixels/s", "cores": threads, "kind": "port",
                                     "sample": f"oracle (reference expressions, torch CPU) fwd+bwd, 5 steps of {CPU_SAMPLE_B}x{H}x{W} px"}
+            try:
+                line["eager_cuda_baseline"] = eager_cuda_baseline(dev)
+            except Exception as e:                       # noqa: BLE001 -- a baseline leg must not sink the bench line
+                line["eager_cuda_baseline"] = {"error": repr(e)[:200]}
         if sweep is not None:
             line["sweep"] = sweep
         if train is not None:
             line["train_step"] = train
+        if world == 1 and not args.no_train_step:
+            try:
+                line["inference"] = inference_bench(dev)
+            except Exception as e:                       # noqa: BLE001
+                line["inference"] = {"error": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -421,6 +460,35 @@ def train_step_bench(dev, group, world, rank, steps: int = 5, warmup: int = 3, c
             f"dp{world}, host images in the timed region (e2e)",
             "kernels": "bf16 channels-last: tcgen05 implicit-GEMM fprop/dgrad/wgrad, fused BN+LeakyReLU+dropout, pool/upsample, Philox perturbations, fused losses (all hand-written sm_100a); torch: autograd glue, fused Adam"
             if compute == "bf16" else "cuDNN fp32 (reference-precision path)"}
+
+
+def inference_bench(dev, batch: int = 64, steps: int = 10, warmup: int = 3):
+    """Row f3: validation / inference forward (UAPS_train.py:367-393) -- main decoder only, BatchNorm folded into the conv
+    weights, LeakyReLU in the conv epilogue.  The reference's README quotes 4.48 ms / 256x256 image for the main decoder
+    (fig_data/decoder-effect.jpg, hardware not stated); reported beside, not as vs_baseline (different metric)."""
+    from uaps_b200.unet import UNet_UAPS
+    torch.manual_seed(1337)
+    model = UNet_UAPS(3, C, compute="bf16").to(dev).eval()
+    x_h = torch.randn(batch, 3, H, W).pin_memory()
+    lab_h = torch.empty((batch, H, W), dtype=torch.uint8).pin_memory()
+
+    def it():
+        logits = model.predict(x_h.to(dev, non_blocking=True))
+        lab_h.copy_(logits.argmax(1).to(torch.uint8), non_blocking=True)      # the label map goes back to the host
+
+    for _ in range(warmup):
+        it()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        it()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_image": ms / batch, "images_per_s": batch * 1e3 / ms, "batch": batch, "ms_per_batch": ms,
+            "config": f"UNet_UAPS.predict 3x{H}x{W} C={C}, bf16 path, eval mode, host images in / uint8 label map out",
+            "published_ms_per_image": 4.48, "published_source": "reference README Fig. 9 (hardware not stated)"}
 
 
 def main():

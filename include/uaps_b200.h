@@ -261,6 +261,14 @@ int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride
                     const float* bias, void* out, int out_c_stride, int out_nchw_f32,
                     int B, int H, int W, int cin1, int cin2, int cout, int ks,
                     void* out2, int out2_c_stride, int split, int fold, cudaStream_t stream);
+/* The same with y = leaky_relu(conv(x) + bias, leaky_slope) in the epilogue (leaky_slope = 1: identity).  With the
+ * running statistics of the following BatchNorm2d folded into weights and bias, one call is a whole eval-mode
+ * conv -> BN -> LeakyReLU layer of ConvBlock (utilities/UAPS_unet.py:36-43): the validation / inference forward
+ * of UAPS_train.py:367-393. */
+int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
+                        const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
+                        int cin1, int cin2, int cout, int ks, void* out2, int out2_c_stride, int split,
+                        int fold, float leaky_slope, cudaStream_t stream);
 
 /* Weight gradient on tcgen05 (MN-major operands straight from the channels-last tensors):
  * dw[co][ci_offset + ci][r][s] += sum_pixels dy[p][co] * x[p + (r-1, s-1)][ci].  dw is fp32 in torch layout

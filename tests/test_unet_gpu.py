@@ -170,3 +170,32 @@ def test_bf16_tcgen05_path():
     # exactness of the data gradient is held to 1e-2 in test_conv_gpu.py.
     assert glob32 >= cud32 - 0.15, (glob32, cud32)
     assert globref > 0.6, globref
+
+
+def test_predict_folded_inference_matches_eval_forward():
+    """Row f3: eval-mode predict() on the bf16 path (BatchNorm folded into the conv weights, LeakyReLU in the conv
+    epilogue) against the fp32 eval-mode main decoder of the same weights, and against the unfolded bf16 layers."""
+    from uaps_b200.unet import UNet_UAPS
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    m32 = UNet_UAPS(3, 4, compute="fp32").to(dev)
+    with torch.no_grad():                                   # non-trivial running statistics and affine parameters
+        for mod in m32.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.7, 1.3); mod.bias.normal_(0, 0.1)
+    m16 = UNet_UAPS(3, 4, compute="bf16").to(dev)
+    m16.load_state_dict(m32.state_dict())
+    m32.eval(); m16.eval()
+    x = torch.randn(4, 3, 64, 96, device=dev)
+    ref = m32.predict(x)
+    got = m16.predict(x)
+    assert got.shape == ref.shape and got.dtype == torch.float32 and got.is_contiguous()
+    rel = (got - ref).norm() / ref.norm()
+    assert rel.item() < 2e-2, rel.item()
+    unfolded = m16._decode16(m16._encode16(x, None), m16.main_decoder)       # eval-mode BN through torch, same bf16 convs
+    rel2 = (got - unfolded).norm() / unfolded.norm()
+    assert rel2.item() < 2e-2, rel2.item()
+    assert (got.argmax(1) == ref.argmax(1)).float().mean().item() > 0.97
+    # the plan is dropped when the weights may change
+    m16.train(); assert m16._infer_plan is None

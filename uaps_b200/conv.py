@@ -99,8 +99,9 @@ class PackedConv:
             self.bias = b.repeat(fold).contiguous()
 
     def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, out_nchw_f32: bool = False,
-                 split: int = 0):
-        """split > 0: return two NHWC tensors holding output channels [0, split) and [split, cout)."""
+                 split: int = 0, slope: float = 1.0):
+        """split > 0: return two NHWC tensors holding output channels [0, split) and [split, cout).
+        slope != 1: LeakyReLU(slope) applied to conv + bias in the kernel's epilogue."""
         L.require_cuda(x1)
         assert x1.dtype == torch.bfloat16 and x1.is_contiguous() and x1.dim() == 4
         B, H, W, c1s = x1.shape
@@ -118,12 +119,12 @@ class PackedConv:
             out = alloc((B, H, W, ocs), dtype=torch.bfloat16, device=x1.device)
         out2 = torch.empty((B, H, W, pad16(self.cout) - split), dtype=torch.bfloat16, device=x1.device) if split else None
         with L.on_device(x1.device):
-            L.check(L.lib().uaps_conv_fprop(x1.data_ptr(), c1s, None if x2 is None else x2.data_ptr(), c2s,
-                                            self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(),
-                                            out.data_ptr(), ocs, int(out_nchw_f32), B, H, W, self.cin1, self.cin2,
-                                            self.cout, self.ks, None if out2 is None else out2.data_ptr(),
-                                            0 if out2 is None else pad16(self.cout) - split, split, self.fold,
-                                            L.stream_ptr()), "uaps_conv_fprop")
+            L.check(L.lib().uaps_conv_fprop_act(x1.data_ptr(), c1s, None if x2 is None else x2.data_ptr(), c2s,
+                                                self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(),
+                                                out.data_ptr(), ocs, int(out_nchw_f32), B, H, W, self.cin1, self.cin2,
+                                                self.cout, self.ks, None if out2 is None else out2.data_ptr(),
+                                                0 if out2 is None else pad16(self.cout) - split, split, self.fold,
+                                                float(slope), L.stream_ptr()), "uaps_conv_fprop_act")
         return out if not split else (out, out2)
 
 

@@ -59,6 +59,7 @@ struct ConvArgs {
     int fold;            // pixel folding factor F (1, 2, 4): the kernel sees [B,H,W/F,F*C] views; only the NCHW / split epilogues care
     int cpp;             // output channels per real pixel in memory (pad16(cout_real))
     int cout_real;
+    float act_slope;     // LeakyReLU slope fused into the epilogue (1 = none): inference with BatchNorm folded into the weights
 };
 
 using namespace uaps::tc;
@@ -388,6 +389,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
                         for (int i = 0; i < 16; ++i) v[i] += (c0 + i < a.cout) ? __ldg(a.bias + c0 + i) : 0.f;
                     }
                 }
+                if (a.act_slope != 1.f) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * a.act_slope;
+                }
                 if (!valid) continue;
                 if (a.out_nchw_f32) {
                     // logits: fp32 NCHW of the REAL image; a folded column block is (sub-pixel, channel)
@@ -592,10 +597,25 @@ UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, in
     return UAPS_OK;
 }
 
+UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
+                                 const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
+                                 int cin1, int cin2, int cout, int ks, void* out2, int out2_c_stride, int split,
+                                 int fold, float leaky_slope, cudaStream_t stream);
+
 UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
                              const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
                              int cin1, int cin2, int cout, int ks, void* out2, int out2_c_stride, int split,
                              int fold, cudaStream_t stream) {
+    return uaps_conv_fprop_act(x1, c1_stride, x2, c2_stride, w_packed, bias, out, out_c_stride, out_nchw_f32, B, H, W, cin1, cin2,
+                               cout, ks, out2, out2_c_stride, split, fold, 1.0f, stream);
+}
+
+// Same with y = leaky_relu(conv(x) + bias, leaky_slope) applied in the epilogue (leaky_slope = 1: identity).  With BatchNorm's
+// running statistics folded into the weights and bias this is a whole eval-mode ConvBlock layer (UAPS_unet.py:36-43) in one kernel.
+UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
+                                 const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
+                                 int cin1, int cin2, int cout, int ks, void* out2, int out2_c_stride, int split,
+                                 int fold, float leaky_slope, cudaStream_t stream) {
     // fold = F > 1: run the virtual convolution on the [B, H, W/F, F*C] views of the same tensors.  Requires the
     // tensors' channel pitch to equal their padded channel count (so F pixels are contiguous) and W % F == 0.
     Plan pl;
@@ -628,6 +648,8 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
     a.out_nchw_f32 = out_nchw_f32; a.bias = bias; a.w_packed = reinterpret_cast<const unsigned char*>(w_packed); a.out = out;
     a.out2 = out2; a.split = split; a.out2_stride = out2_c_stride;
     a.fold = fold; a.cpp = (fold > 1 || out2 != nullptr) ? cpp : cout; a.cout_real = cout_real;
+    a.act_slope = leaky_slope;
+    if (leaky_slope != 1.0f && getenv("UAPS_CONV_V1") != nullptr) return UAPS_EINVAL;      // the v1 kernel has no activation epilogue
     if (out2 != nullptr && (out_nchw_f32 || (split % 16) != 0 || split <= 0 || split >= cpp || (out2_c_stride % 8) != 0 ||
                             !aligned_to(out2, 16) || getenv("UAPS_CONV_V1") != nullptr))
         return UAPS_EINVAL;

@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from . import perturb as P
 from .bn_act import bn_lrelu_dropout
-from .conv import conv_bf16, pad16, to_nhwc_bf16
+from .conv import PackedConv, conv_bf16, pad16, to_nhwc_bf16
 from .resample import maxpool2, upsample2x
 
 FT_CHNS = (16, 32, 64, 128, 256)            # UAPS_unet.py:212
@@ -176,10 +176,68 @@ class UNet_UAPS(nn.Module):
             outs.append(self._decode16(pf, self.get_submodule(f"aux_decoder{a}")))
         return tuple(outs) if self.n_aux else outs[0]
 
+    # ---- inference: BatchNorm folded into the convolutions, LeakyReLU in the conv epilogue --------------------
+    @staticmethod
+    def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+        """Eval-mode BN(conv(x)) as one convolution: w' = w * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(var + eps) + beta."""
+        s = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        w = conv.weight.detach().float() * s.view(-1, 1, 1, 1)
+        b = (conv.bias.detach().float() - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+        return w.contiguous(), b.contiguous()
+
+    def _inference_plan(self):
+        """Packed, BN-folded layers of encoder + main decoder (built lazily, dropped by train() / load_state_dict())."""
+        plan = getattr(self, "_infer_plan", None)
+        if plan is not None:
+            return plan
+        def block(blk, cin_split=None):
+            cc = blk.conv_conv
+            w0, b0 = self._fold_bn(cc.get_submodule("0"), cc.get_submodule("1"))
+            w4, b4 = self._fold_bn(cc.get_submodule("4"), cc.get_submodule("5"))
+            return PackedConv(w0, b0, cin_split=cin_split), PackedConv(w4, b4)
+        enc = [block(self.encoder.in_conv)] + \
+              [block(self.encoder.get_submodule(f"down{lvl}").maxpool_conv.get_submodule("1")) for lvl in range(1, 5)]
+        dec = []
+        md = self.main_decoder
+        for i in range(1, 5):
+            up = md.get_submodule(f"up{i}")
+            c2 = FT_CHNS[4 - i]
+            dec.append((PackedConv(up.conv1x1.weight, up.conv1x1.bias), *block(up.conv, cin_split=c2)))
+        out = PackedConv(md.out_conv.weight, md.out_conv.bias)
+        self._infer_plan = (enc, dec, out)
+        return self._infer_plan
+
+    def train(self, mode: bool = True):
+        self._infer_plan = None                       # weights are about to change: drop the folded copies
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kw):
+        self._infer_plan = None
+        return super().load_state_dict(*args, **kw)
+
     @torch.no_grad()
     def predict(self, x: torch.Tensor) -> torch.Tensor:
         """Validation / inference fast path (UAPS_train.py:377, UAPS-Testing.ipynb): the main decoder's logits only.
-        The reference runs -- and perturbs -- all three auxiliary decoders here and throws their outputs away."""
+        The reference runs -- and perturbs -- all three auxiliary decoders here and throws their outputs away.
+
+        bf16 path in eval mode: BatchNorm's running statistics are folded into the conv weights and LeakyReLU runs in
+        the conv epilogue (``uaps_conv_fprop_act``), so the whole forward is 23 tcgen05 conv launches, 4 max-pools and
+        4 upsamples -- no BatchNorm or activation pass touches HBM.  In training mode (batch statistics) and on the
+        fp32 path it falls back to the ordinary layers."""
+        if self.compute == "bf16" and not self.training:
+            enc, dec, out = self._inference_plan()
+            cur = to_nhwc_bf16(x)                                            # [B,H,W,16]
+            feats = []
+            for lvl, (c0, c4) in enumerate(enc):
+                if lvl:
+                    cur = maxpool2(cur.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+                cur = c4(c0(cur, slope=0.01), slope=0.01)
+                feats.append(cur)
+            cur = feats[4]
+            for i, (c1x1, c0, c4) in enumerate(dec, start=1):
+                up = upsample2x(c1x1(cur).permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+                cur = c4(c0(feats[4 - i], up, slope=0.01), slope=0.01)
+            return out(cur, out_nchw_f32=True)
         if self.compute == "bf16":
             return self._decode16(self._encode16(x, None), self.main_decoder)
         return self.decode(self.encode(x), self.main_decoder)
