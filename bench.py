@@ -270,18 +270,24 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     # ---- timed region: device-resident inputs ---------------------------------------------------
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    # Per-kernel events on every EV_EVERY-th step only (three records: start, after pass 1 + fold/finalize, end): an event
+    # record between two launches cancels their programmatic-dependent-launch overlap, so the other steps run as the
+    # library is used in a training loop.  `value` is from the outer pair of events around all K steps.
+    EV_EVERY = 4
+    evs = {i: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for i in range(0, args.steps, EV_EVERY)}
     barrier()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
-        step(evs[i])
+        ev = evs.get(i)
+        if ev:
+            ev[0].record()
+        step(ev[1:] if ev else None)
     t_end.record()
     barrier()
     ms_total = t_start.elapsed_time(t_end)
-    starts = [t_start] + [e[1] for e in evs[:-1]]
-    t1 = sum(s.elapsed_time(e[0]) for s, e in zip(starts, evs)) / args.steps      # pass 1 + fold/finalize (+ all-reduce)
-    t2 = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps                   # pass 2
+    t1 = sum(e[0].elapsed_time(e[1]) for e in evs.values()) / len(evs)      # pass 1 + fold/finalize (+ exchange)
+    t2 = sum(e[1].elapsed_time(e[2]) for e in evs.values()) / len(evs)      # pass 2
 
     # ---- e2e: public API, pinned host logits -> H2D -> fwd + bwd -> D2H loss scalars ---------------
     zh = [torch.empty((B, C, H, W), dtype=torch.float32).pin_memory() for _ in range(K)]
@@ -359,6 +365,7 @@ def run_ours(args):
             "e2e": {"value": N * world * e2e_steps / (ms_e2e * 1e-3), "unit": "pixels/s",
                     "h2d_bytes_per_step": 4 * K * C * N, "d2h_bytes_per_step": 12, "steps": e2e_steps,
                     "api": "uaps_b200.losses.uaps_unlabeled_loss + backward, pinned host logits"},
+            "kernel_events": f"sampled on every {EV_EVERY}th step ({len(evs)} of {args.steps})",
             "gpu_launches": (3 if (world == 1 or xchg is not None) else 4) * args.steps,   # pass1, fold(+exchange)+finalize, pass2
             "clocks": clocks,
         }

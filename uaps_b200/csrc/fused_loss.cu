@@ -112,22 +112,10 @@ __global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const
                                                                             int C, double N, float cw1, float cw2, int supervised,
                                                                             float* __restrict__ sc, int nsc) {
     __shared__ double s_sums[XCHG_SLOT];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = warp; i < S; i += 32) {                         // local fold, as loss_fold_finalize_kernel
-        const float* row = partials + (size_t)i * LOSS_MAX_BLOCKS;
-        float v[LOSS_MAX_BLOCKS / kWarp];
-#pragma unroll
-        for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) {
-            const unsigned blk = u * kWarp + lane;
-            v[u] = (blk < nblocks) ? __ldcg(row + blk) : 0.f;
-        }
-        double r = 0.0;
-#pragma unroll
-        for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) r += (double)v[u];
-        r = warp_sum(r);
-        if (lane == 0) s_sums[i] = r;
-    }
-    __syncthreads();
+    __shared__ double s_term[KMAX * CMAX];
+    pdl_trigger();
+    pdl_wait();
+    cta_fold_rows(partials, S, nblocks, s_sums);                 // local fold, as loss_fold_finalize_kernel
     const int ph = x.epoch & 1;
     // scatter: my sums into slot [ph][rank] of every mailbox (peer stores travel over NVLink)
     for (int t = threadIdx.x; t < x.world * S; t += blockDim.x) {
@@ -167,7 +155,7 @@ __global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const
         sums[threadIdx.x] = r;
     }
     __syncthreads();
-    if (threadIdx.x == 0) finalize_from_sums(s_sums, K, C, N, cw1, cw2, supervised, sc);
+    cta_finalize(s_sums, K, C, N, cw1, cw2, supervised, sc, s_term);
 }
 
 }  // namespace
@@ -216,13 +204,16 @@ static int loss_pass1_impl(const float* const* z, int K, int B, int C, int64_t H
     if (rc != UAPS_OK) return rc;
     const int S = sums_count(K, C);
     if (xchg != nullptr)
-        loss_fold_exchange_finalize_kernel<<<1, 1024, 0, stream>>>(partials, S, (unsigned)nblocks, sums, *xchg, K, C, (double)N_global,
-                                                                   cw1, cw2, labels != nullptr, scalars, scalars_count(K, C));
+        rc = (int)launch_pdl(loss_fold_exchange_finalize_kernel, dim3(1), dim3(1024), stream, pdl_enabled(), (const float*)partials, S,
+                             (unsigned)nblocks, sums, *xchg, K, C, (double)N_global, cw1, cw2, (int)(labels != nullptr), scalars,
+                             scalars_count(K, C));
     else if (scalars != nullptr)
-        loss_fold_finalize_kernel<<<1, 1024, 0, stream>>>(partials, S, (unsigned)nblocks, sums, K, C, (double)N_global, cw1, cw2,
-                                                          labels != nullptr, scalars);
+        rc = (int)launch_pdl(loss_fold_finalize_kernel, dim3(1), dim3(1024), stream, pdl_enabled(), (const float*)partials, S,
+                             (unsigned)nblocks, sums, K, C, (double)N_global, cw1, cw2, (int)(labels != nullptr), scalars);
     else
-        loss_fold_kernel<<<ceil_div(S, 256 / kWarp), 256, 0, stream>>>(partials, S, (unsigned)nblocks, sums);
+        rc = (int)launch_pdl(loss_fold_kernel, dim3(ceil_div(S, 256 / kWarp)), dim3(256), stream, pdl_enabled(), (const float*)partials,
+                             S, (unsigned)nblocks, sums);
+    if (rc != 0) return rc;
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -308,7 +299,9 @@ UAPS_API int uaps_loss_finalize(const double* sums_global, int K, int C, int64_t
     if (sums_global == nullptr || scalars == nullptr || N_global <= 0) return UAPS_EINVAL;
     if (K < 1 || K > KMAX || C < 2 || C > CMAX) return UAPS_ERANGE;
     if (!aligned_to(sums_global, 8) || !aligned_to(scalars, 4)) return UAPS_EALIGN;
-    loss_finalize_kernel<<<1, 32, 0, stream>>>(sums_global, K, C, (double)N_global, cw1, cw2, supervised, scalars);
+    const int rc = (int)launch_pdl(loss_finalize_kernel, dim3(1), dim3(32), stream, pdl_enabled(), sums_global, K, C, (double)N_global,
+                                   cw1, cw2, supervised, scalars);
+    if (rc != 0) return rc;
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }

@@ -12,6 +12,7 @@
 // (cunn_SpatialSoftMaxForward), then separately rounded w*p multiplies and left-associated adds
 // (one ATen kernel each in the reference, so no FMA contraction), then first-maximum argmax.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 namespace uaps {
@@ -31,6 +32,30 @@ __host__ __device__ constexpr int min_ctas(int K, int C, int VEC, bool pass1) {
     return need <= 124 ? 4 : (need <= 176 ? 3 : 2);
 }
 __host__ __device__ constexpr int scalars_count(int K, int C) { return UAPS_SC_BASE + 4 * K + 2 * K * C; }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// pass 1 -> fold/finalize -> pass 2 are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's
+// CTAs may become resident while its predecessor is still draining, and block in pdl_wait() until the predecessor
+// has completed and flushed.  Everything a kernel reads that a predecessor may have written is read after pdl_wait();
+// pass 2 issues its first logits loads before it (the logits were already consumed by pass 1 of the same loss, so they
+// are older than any predecessor's output), which hides the fold/finalize kernel and two launch gaps behind them.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("UAPS_LOSS_PDL"); return e == nullptr || atoi(e) != 0; }();
+    return on;
+}
 
 struct LossArgs {
     const float* z[KMAX];
@@ -332,6 +357,8 @@ __global__ void __launch_bounds__(LOSS_THREADS, min_ctas(K, C, PF ? 2 * VEC : VE
 loss_pass1_kernel(const __grid_constant__ LossArgs a, float* __restrict__ partials) {
     constexpr int S = sums_count(K, C);
     __shared__ float s_red[LOSS_THREADS / kWarp][S];
+    pdl_wait();                       // the logits may be the previous kernel's output (out_conv epilogue)
+    pdl_trigger();                    // the fold kernel's CTA may take the first SM slot that frees up
 
     float w[K];
 #pragma unroll
@@ -404,6 +431,8 @@ loss_pass1_kernel(const __grid_constant__ LossArgs a, float* __restrict__ partia
 // lane's loads issued together (unrolled, predicated) so a row costs one L2 round trip.
 __global__ void __launch_bounds__(256) loss_fold_kernel(const float* __restrict__ partials, int S, unsigned nblocks,
                                                         double* __restrict__ sums) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (256 / kWarp) + (threadIdx.x >> 5);
     if (i >= S) return;
@@ -421,6 +450,83 @@ __global__ void __launch_bounds__(256) loss_fold_kernel(const float* __restrict_
     if (lane == 0) sums[i] = r;
 }
 
+// One CTA of 1024 threads folds partials[S][LOSS_MAX_BLOCKS] into s_sums[S] (fp64): a HALF-warp per sum row, so the
+// up-to-64 rows go in one pass; every lane's loads are issued together (unrolled, predicated), the adds run in a fixed
+// order (deterministic).  Ends with __syncthreads().
+__device__ __forceinline__ void cta_fold_rows(const float* __restrict__ partials, int S, unsigned nblocks, double* s_sums) {
+    constexpr int HALF = 16, PER_LANE = LOSS_MAX_BLOCKS / HALF;
+    const int sub = threadIdx.x & (HALF - 1);
+    for (int base = (threadIdx.x >> 5) * 2; base < S; base += 2 * (1024 / 32)) {    // warp-uniform trip count (S may be odd)
+        const int i = base + ((threadIdx.x >> 4) & 1);
+        const bool live = i < S;
+        const float* row = partials + (size_t)(live ? i : 0) * LOSS_MAX_BLOCKS;
+        float v[PER_LANE];
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) {
+            const unsigned blk = u * HALF + sub;
+            v[u] = (live && blk < nblocks) ? __ldcg(row + blk) : 0.f;
+        }
+        double r = 0.0;
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) r += (double)v[u];
+#pragma unroll
+        for (int o = HALF / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (live && sub == 0) s_sums[i] = r;
+    }
+    __syncthreads();
+}
+
+// Cooperative finalize (whole CTA, >= K*C threads): the K*C fp64 divisions of the Dice terms run in parallel, thread 0
+// combines them in the same order as finalize_from_sums.  s_term: K*C doubles of shared memory.
+__device__ __forceinline__ void cta_finalize(const double* sums, int K, int C, double N, float cw1, float cw2, int supervised,
+                                             float* sc, double* s_term) {
+    const double* sI = sums + 3 * K;
+    const double* sP = sums + 3 * K + K * C;
+    const double* sT = sums + 3 * K + 2 * K * C;
+    float* Ikc = sc + UAPS_SC_BASE + 4 * K;
+    float* Card = Ikc + K * C;
+    const int t = threadIdx.x;
+    if (t < K * C) {
+        const double card = sP[t] + sT[t % C];
+        s_term[t] = 2.0 * sI[t] / (card + 1e-7);                          // pytorch_losses.py:88
+        Ikc[t] = (float)sI[t];
+        Card[t] = (float)card;
+    }
+    __syncthreads();
+    if (t != 0) return;
+    const double* sCE = sums;
+    const double* sE = sums + K;
+    const double* sV = sums + 2 * K;
+    float* ps = sc + UAPS_SC_BASE;
+    float* Eb = ps + K;
+    float* CE = Eb + K;
+    float* DI = CE + K;
+    const double invN = 1.0 / N;
+    double ps_loss = 0.0, unc = 0.0, mce = 0.0, mdi = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double ce = sCE[k] / N;
+        double d = 0.0;
+        for (int c = 0; c < C; ++c) d += s_term[k * C + c];
+        const double dice = 1.0 - d / C;
+        const double psk = 0.5 * (ce + dice);                          // UAPS_train.py:259-262
+        const double eb = supervised ? 1.0 : sE[k] / N;
+        ps[k] = (float)psk; Eb[k] = (float)eb; CE[k] = (float)ce; DI[k] = (float)dice;
+        ps_loss += psk * eb;                                           // :265-268 (scalar x mean(E))
+        unc += sV[k] / N;
+        mce += (double)(float)ce; mdi += (double)(float)dice;
+    }
+    ps_loss /= K;                                                       // :277
+    unc /= K;                                                           // :241-243
+    sc[UAPS_SC_PS_LOSS] = (float)ps_loss;
+    sc[UAPS_SC_L_UNCERT] = supervised ? 0.f : (float)unc;
+    sc[UAPS_SC_LOSS_U] = supervised ? (float)ps_loss : (float)((double)cw1 * ps_loss + (double)cw2 * unc);
+    sc[UAPS_SC_CW1] = supervised ? 1.f : cw1;
+    sc[UAPS_SC_CW2] = supervised ? 0.f : cw2;
+    sc[UAPS_SC_INV_N] = (float)invN;
+    sc[UAPS_SC_MEAN_CE] = (float)(mce / K);                             // :216 total_loss_ce
+    sc[UAPS_SC_MEAN_DICE] = (float)(mdi / K);                           // :217 total_loss_dice
+}
+
 // Single-rank fast path: fold + finalize in one launch (one CTA of 32 warps, a warp per sum row, then thread 0
 // turns the sums into the scalars).  Saves a kernel and a launch gap per step versus fold -> finalize.
 __device__ void finalize_from_sums(const double* sums, int K, int C, double N, float cw1, float cw2, int supervised, float* sc);
@@ -429,23 +535,12 @@ __global__ void __launch_bounds__(1024) loss_fold_finalize_kernel(const float* _
                                                                    double* __restrict__ sums, int K, int C, double N, float cw1,
                                                                    float cw2, int supervised, float* __restrict__ sc) {
     __shared__ double s_sums[3 * KMAX + 2 * KMAX * CMAX + CMAX];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = warp; i < S; i += 32) {
-        const float* row = partials + (size_t)i * LOSS_MAX_BLOCKS;
-        float v[LOSS_MAX_BLOCKS / kWarp];
-#pragma unroll
-        for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) {
-            const unsigned blk = u * kWarp + lane;
-            v[u] = (blk < nblocks) ? __ldcg(row + blk) : 0.f;
-        }
-        double r = 0.0;
-#pragma unroll
-        for (int u = 0; u < LOSS_MAX_BLOCKS / kWarp; ++u) r += (double)v[u];
-        r = warp_sum(r);
-        if (lane == 0) { s_sums[i] = r; sums[i] = r; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) finalize_from_sums(s_sums, K, C, N, cw1, cw2, supervised, sc);
+    __shared__ double s_term[KMAX * CMAX];
+    pdl_trigger();                    // pass 2 may start prefetching its logits now; it waits for THIS kernel before using sc
+    pdl_wait();                       // partials of pass 1
+    cta_fold_rows(partials, S, nblocks, s_sums);
+    if (threadIdx.x < S) sums[threadIdx.x] = s_sums[threadIdx.x];
+    cta_finalize(s_sums, K, C, N, cw1, cw2, supervised, sc, s_term);
 }
 
 __device__ void finalize_from_sums(const double* sums, int K, int C, double N, float cw1, float cw2, int supervised, float* sc) {
@@ -494,6 +589,8 @@ __device__ void finalize_from_sums(const double* sums, int K, int C, double N, f
 
 __global__ void loss_finalize_kernel(const double* __restrict__ sums, int K, int C, double N,
                                      float cw1, float cw2, int supervised, float* __restrict__ sc) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     finalize_from_sums(sums, K, C, N, cw1, cw2, supervised, sc);
 }
@@ -581,8 +678,6 @@ template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF>
 __global__ void __launch_bounds__(LOSS_THREADS, min_ctas(K, C, PF ? 2 * VEC : VEC, false))
 loss_pass2_kernel(const __grid_constant__ LossArgs a, const float* __restrict__ sc, const float* __restrict__ grad_out) {
     __shared__ GradConsts<K, C> gc;
-    if (threadIdx.x == 0) load_grad_consts<K, C>(gc, sc, grad_out);
-    __syncthreads();
 
     float w[K];
 #pragma unroll
@@ -593,7 +688,11 @@ loss_pass2_kernel(const __grid_constant__ LossArgs a, const float* __restrict__ 
     const unsigned stride = gridDim.x * LOSS_THREADS;
     unsigned g = blockIdx.x * LOSS_THREADS + threadIdx.x;
     float zn[PF ? K : 1][PF ? C : 1][PF ? VEC : 1];
-    if constexpr (PF) { if (g < a.ngroups) load_group<K, C, VEC>(a, g, zn); }
+    if constexpr (PF) { if (g < a.ngroups) load_group<K, C, VEC>(a, g, zn); }     // in flight while the predecessor drains
+    pdl_wait();                       // scalars (fold/finalize), upstream gradient, labels
+    pdl_trigger();
+    if (threadIdx.x == 0) load_grad_consts<K, C>(gc, sc, grad_out);
+    __syncthreads();
     for (; g < a.ngroups; g += stride) {
         const unsigned b = g / a.groups_per_image;
         const unsigned hw = (g - b * a.groups_per_image) * VEC;
@@ -668,13 +767,15 @@ inline int launch_reg(bool pass2, LossArgs a, float* partials, const float* sc, 
         static const int grid_cap = grid_for(kern, 0x7fffffffu);       // occupancy query once per instantiation
         const long long want = ceil_div<long long>(a.ngroups, LOSS_THREADS);
         *nblocks = (int)(want < grid_cap ? want : grid_cap);
-        kern<<<*nblocks, LOSS_THREADS, 0, st>>>(a, partials);
+        const cudaError_t e = launch_pdl(kern, dim3(*nblocks), dim3(LOSS_THREADS), st, pdl_enabled(), a, partials);
+        if (e != cudaSuccess) return (int)e;
     } else {
         auto kern = loss_pass2_kernel<K, C, VEC, SUP, EXACT, PF>;
         static const int grid_cap = grid_for(kern, 0x7fffffffu);
         const long long want = ceil_div<long long>(a.ngroups, LOSS_THREADS);
         *nblocks = (int)(want < grid_cap ? want : grid_cap);
-        kern<<<*nblocks, LOSS_THREADS, 0, st>>>(a, sc, go);
+        const cudaError_t e = launch_pdl(kern, dim3(*nblocks), dim3(LOSS_THREADS), st, pdl_enabled(), a, sc, go);
+        if (e != cudaSuccess) return (int)e;
     }
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
