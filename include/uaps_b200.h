@@ -278,6 +278,14 @@ int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int x_c_stri
                     int B, int H, int W, int cout, int cin, int cin_total, int ci_offset, int ks,
                     cudaStream_t stream);
 
+/* ---- optimizer (UAPS_train.py:112, 292: torch.optim.Adam(model.parameters(), lr) and its step()) -----------------
+ * One Adam step over flat fp32 buffers of n elements (parameters, gradients, first and second moments; 16-byte
+ * aligned): torch's update rule with its defaults' structure (no weight decay, no amsgrad):
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps).
+ * step = 1, 2, 3, ...; grad_scale multiplies g first (1 when the gradient is already that of the global loss). */
+int uaps_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t step, float lr, float beta1,
+                   float beta2, float eps, float grad_scale, cudaStream_t stream);
+
 /* On-device confusion matrix behind utilities/metrics.py (pixel_accuracy :8, mIoU :16, mDice :40):
  * conf[label * C + argmax(softmax(logits))] += 1 per pixel (labels outside [0,C) ignored).  logits [B,C,HW] fp32,
  * labels [B,HW] int64, conf C*C uint64 ACCUMULATED into. */

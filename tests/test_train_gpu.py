@@ -80,3 +80,42 @@ def test_bf16_path_trains_like_fp32_path():
     assert a[-1] < 0.9 * a[0] and b[-1] < 0.9 * b[0], (a, b)
     for s, (u, v) in enumerate(zip(a, b)):
         assert abs(u - v) <= 0.05 * abs(u), (s, u, v)
+
+
+def test_flat_adam_matches_torch_adam_and_shares_its_checkpoint_format():
+    """Row f4: FlatAdam (one kernel over flat buffers, uaps_adam_step) against torch.optim.Adam on the same gradients,
+    and state_dict round trips in both directions (the reference's checkpoint stores optimizer_1.state_dict(), :447)."""
+    from uaps_b200.train import FlatAdam, FlatGradBuffer
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    shapes = [(16, 3, 3, 3), (16,), (7,), (32, 16, 3, 3), (2,), (4, 16, 3, 3)]
+    ours = [torch.nn.Parameter(torch.randn(*s, device=dev)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    buf = FlatGradBuffer(ours)
+    opt = FlatAdam(buf, lr=1e-2)
+    topt = torch.optim.Adam(ref, lr=1e-2)
+    assert all(p.data_ptr() % 256 == 0 and p.grad.data_ptr() % 256 == 0 for p in ours)
+    for it in range(7):
+        if it == 4:                                          # a scheduler lowers the rate in place (:113)
+            opt.param_groups[0]["lr"] = 3e-3
+            topt.param_groups[0]["lr"] = 3e-3
+        for p, r in zip(ours, ref):
+            g = torch.randn_like(r) * (0.1 + it)
+            p.grad.copy_(g)
+            r.grad = g.clone()
+        opt.step(); topt.step()
+    for p, r in zip(ours, ref):
+        torch.testing.assert_close(p.detach(), r.detach(), rtol=2e-6, atol=2e-7)
+    # torch -> ours -> torch: the moments and the step count survive
+    sd_t = topt.state_dict()
+    opt2 = FlatAdam(FlatGradBuffer([torch.nn.Parameter(p.detach().clone()) for p in ref]), lr=1.0)
+    opt2.load_state_dict(sd_t)
+    assert opt2.step_count == 7 and opt2.param_groups[0]["lr"] == 3e-3
+    sd_o = opt2.state_dict()
+    assert set(sd_o) == {"state", "param_groups"} and set(sd_o["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    for i in range(len(shapes)):
+        torch.testing.assert_close(sd_o["state"][i]["exp_avg"], sd_t["state"][i]["exp_avg"])
+        torch.testing.assert_close(sd_o["state"][i]["exp_avg_sq"], sd_t["state"][i]["exp_avg_sq"])
+    topt2 = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ref], lr=1.0)
+    topt2.load_state_dict(sd_o)                              # torch accepts our dict
+    assert topt2.param_groups[0]["lr"] == 3e-3

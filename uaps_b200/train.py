@@ -40,20 +40,25 @@ class UAPSConfig:
     consistency_rampup: float = 200.0
     iters_per_ramp_epoch: int = 80       # ``iter_num // 80`` (:279-280); 60/40/50 in the dataset variants
     seed: int = 1337
+    optimizer: str = "uaps"              # "uaps": FlatAdam (one kernel over flat buffers); "torch": torch.optim.Adam(fused=True)
 
 
 class FlatGradBuffer:
     """All parameter gradients as views of one contiguous fp32 buffer: zeroed with one memset,
-    all-reduced with one NCCL call (14.9 MB for the 3.71 M parameters of UNet_UAPS)."""
+    all-reduced with one NCCL call (14.9 MB for the 3.71 M parameters of UNet_UAPS).  Every parameter's slot starts
+    on a 256-byte boundary (the kernels take 16-byte vector loads of biases and BN parameters)."""
+
+    ALIGN = 64                            # elements: every parameter starts on a 256-byte boundary, like a torch allocation
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
-        off = 0
+        self.offsets, n = [], 0
         for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
     def zero(self):
         self.flat.zero_()
@@ -63,11 +68,79 @@ class FlatGradBuffer:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
 
+class FlatAdam:
+    """torch.optim.Adam(params, lr) (UAPS_train.py:112) as ONE kernel over flat buffers (uaps_adam_step).
+
+    The parameters are re-homed into one contiguous fp32 buffer (each ``p.data`` becomes a view of it, like the
+    ``.grad`` views of ``FlatGradBuffer``), so the update of all 3.71 M parameters is a single streaming launch.
+    ``state_dict()`` / ``load_state_dict()`` speak torch.optim.Adam's format (state[i] = step / exp_avg / exp_avg_sq,
+    one param group), so the reference's checkpoints (:443-450) round-trip through either optimizer."""
+
+    def __init__(self, grads: "FlatGradBuffer", lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.grads, self.params = grads, grads.params
+        self.lr, self.betas, self.eps, self.step_count = float(lr), (float(betas[0]), float(betas[1])), float(eps), 0
+        dev = grads.flat.device
+        self.flat_p = torch.zeros_like(grads.flat)     # same layout as the gradients (256-byte aligned slots, zero padding)
+        with torch.no_grad():
+            for p, off in zip(self.params, grads.offsets):
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view                          # parameter storage now lives in the flat buffer
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.param_groups = [{"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                              "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                              "fused": None, "params": list(range(len(self.params)))}]
+        assert dev.type == "cuda", "uaps_b200 has no CPU path"
+
+    @torch.no_grad()
+    def step(self):
+        from . import _lib as L
+        self.step_count += 1
+        lr = float(self.param_groups[0]["lr"])          # a scheduler (ReduceLROnPlateau, :113) edits the group in place
+        with L.on_device(self.flat_p.device):
+            L.check(L.lib().uaps_adam_step(self.flat_p.data_ptr(), self.grads.flat.data_ptr(), self.exp_avg.data_ptr(),
+                                           self.exp_avg_sq.data_ptr(), self.flat_p.numel(), self.step_count, lr,
+                                           self.betas[0], self.betas[1], self.eps, 1.0, L.stream_ptr()), "uaps_adam_step")
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.grads.zero()
+
+    def state_dict(self):
+        state = {}
+        for i, (p, off) in enumerate(zip(self.params, self.grads.offsets)):
+            n = p.numel()
+            if self.step_count > 0:
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+        return {"state": state, "param_groups": [dict(g) for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        steps = set()
+        for i, (p, off) in enumerate(zip(self.params, self.grads.offsets)):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + n].view_as(p).copy_(st["exp_avg"])
+                self.exp_avg_sq[off:off + n].view_as(p).copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise RuntimeError("FlatAdam keeps one step count for all parameters; the checkpoint has several")
+        self.step_count = steps.pop() if steps else 0
+        g = sd["param_groups"][0]
+        self.param_groups[0].update({k: g[k] for k in ("lr", "betas", "eps") if k in g})
+        self.betas, self.eps = tuple(float(b) for b in self.param_groups[0]["betas"]), float(self.param_groups[0]["eps"])
+
+
 class UAPSTrainer:
     def __init__(self, model: torch.nn.Module, cfg: Optional[UAPSConfig] = None, group=None):
         self.model, self.cfg, self.group = model, cfg or UAPSConfig(), group
         self.grads = FlatGradBuffer(model.parameters())
-        self.optimizer = torch.optim.Adam(self.grads.params, lr=self.cfg.base_lr, fused=True)   # :112
+        if self.cfg.optimizer == "torch":
+            self.optimizer = torch.optim.Adam(self.grads.params, lr=self.cfg.base_lr, fused=True)   # :112 (library kernel)
+        else:
+            self.optimizer = FlatAdam(self.grads, lr=self.cfg.base_lr)                              # :112, one own kernel
         self.iter_num = 0
         # identical Dirichlet draws on every rank (the reference draws once per iteration on the host, :251)
         self.rng = np.random.default_rng(self.cfg.seed)
