@@ -493,7 +493,23 @@ def inference_bench(dev, batch: int = 64, steps: int = 10, warmup: int = 3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+
+    # latency mode: one image per call, host image in, label map out; plain launches vs the captured CUDA graph
+    x1_h = torch.randn(1, 3, H, W).pin_memory()
+    lab1_h = torch.empty((1, H, W), dtype=torch.uint8).pin_memory()
+    lat = {}
+    for name, fn in (("launches", model.predict), ("cuda_graph", model.predict_graphed)):
+        def one():
+            lab1_h.copy_(fn(x1_h.to(dev, non_blocking=True)).argmax(1).to(torch.uint8), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(5):
+            one()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            one()
+        lat[name] = (time.perf_counter() - t0) / 50 * 1e3
     return {"ms_per_image": ms / batch, "images_per_s": batch * 1e3 / ms, "batch": batch, "ms_per_batch": ms,
+            "latency_ms_batch1": lat,
             "config": f"UNet_UAPS.predict 3x{H}x{W} C={C}, bf16 path, eval mode, host images in / uint8 label map out",
             "published_ms_per_image": 4.48, "published_source": "reference README Fig. 9 (hardware not stated)"}
 

@@ -199,3 +199,18 @@ def test_predict_folded_inference_matches_eval_forward():
     assert (got.argmax(1) == ref.argmax(1)).float().mean().item() > 0.97
     # the plan is dropped when the weights may change
     m16.train(); assert m16._infer_plan is None
+
+
+def test_predict_graphed_replays_the_same_forward():
+    from uaps_b200.unet import UNet_UAPS
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    m = UNet_UAPS(3, 4, compute="bf16").to(dev).eval()
+    for b in (1, 3):
+        x1, x2 = torch.randn(b, 3, 64, 64, device=dev), torch.randn(b, 3, 64, 64, device=dev)
+        r1, r2 = m.predict(x1), m.predict(x2)
+        g1 = m.predict_graphed(x1).clone()
+        g2 = m.predict_graphed(x2).clone()                      # second call: pure replay with new input
+        assert torch.equal(g1, r1) and torch.equal(g2, r2)
+    assert len(m._graphs) == 2
+    m.train(); assert "_graphs" not in m.__dict__

@@ -28,6 +28,9 @@ __host__ __device__ constexpr int sums_count(int K, int C) { return 3 * K + 2 * 
 // CTAs (of 128 threads) per SM the register allocator is asked to fit: estimated live registers =
 // the K*C*VEC logits + (pass 1) the running sums + ~64 of per-pixel state
 __host__ __device__ constexpr int min_ctas(int K, int C, int VEC, bool pass1) {
+#ifdef UAPS_P1_CTAS
+    if (pass1) return UAPS_P1_CTAS;       // tuning experiments only
+#endif
     const int need = K * C * VEC + (pass1 ? sums_count(K, C) : K * C) + 64;
     return need <= 124 ? 4 : (need <= 176 ? 3 : 2);
 }
