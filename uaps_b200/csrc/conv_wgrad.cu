@@ -22,7 +22,7 @@ using namespace uaps::tc;
 
 constexpr int TILE_H = 16, TILE_W = 8, TILE_M = 128;
 constexpr int THREADS = 128;
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 8;
 
 struct WgradArgs {
     int B, H, W;
@@ -34,6 +34,7 @@ struct WgradArgs {
     int two_boxes;                                 // cout > 64: second 64-channel box carries data
     float* dw;
     int m_rows;                                    // MMA M: 64 when the taps x channel-chunk rows fit (halves the A-operand fetch), else 128
+    int stages;                                    // depth of the TMA -> MMA ring (3..8)
     int fused_r;                                   // 1: the vertical taps ride in N (dY box with a row halo), one MMA per k-step
 };
 
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(THREADS)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                   const __grid_constant__ WgradArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], done_bar;
+    const int STAGES = a.stages;
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,7 +268,15 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     const int row_a = a.a_ch * 2, row_b = a.n_chunk * 2;
     const int dy_rows = TILE_H + (a.fused_r ? ks - 1 : 0), x_rows = TILE_H + (a.fused_r ? 0 : ks - 1);
     const int a_bytes = (a.two_boxes ? 2 : 1) * dy_rows * TILE_W * row_a, b_bytes = x_rows * (TILE_W + ks - 1) * row_b;
-    const size_t smem = (size_t)STAGES * ((a_bytes + b_bytes + 1023) & ~1023) + 1024;
+    // ring depth: small-channel tiles are ~10 KB, so a deeper ring is cheap and hides the TMA latency better (measured)
+    static const int stages_env = [] { const char* e = getenv("UAPS_WGRAD_STAGES"); return e ? atoi(e) : 0; }();
+    const int stage_sz = (a_bytes + b_bytes + 1023) & ~1023;
+    // measured (B=64, tools/gpu_probe_layers.py): 3x3 16-channel layers 100 -> 86 us with 8 stages, 32-channel 62.5 -> 58.4 us
+    // with 6; the 1x1 and >= 64-channel layers are best at 3 (deeper rings only cost them resident CTAs)
+    const int auto_stages = ks == 3 && stage_sz <= 12 * 1024 ? 8 : (ks == 3 && stage_sz <= 24 * 1024 ? 6 : 3);
+    a.stages = stages_env >= 2 && stages_env <= MAX_STAGES ? stages_env : auto_stages;
+    while (a.stages > 2 && (size_t)a.stages * stage_sz > 200 * 1024) --a.stages;
+    const size_t smem = (size_t)a.stages * stage_sz + 1024;
     // split-K: enough CTAs to fill the machine (as many as fit per SM by shared memory and the 512 TMEM columns),
     // but at least 4 pixel tiles per CTA so the 9 * n_chunk * Cout reductions of the epilogue stay amortised
     int tmem_cols = 32;
