@@ -34,7 +34,7 @@ namespace conv {
 
 constexpr int TILE_H = 16, TILE_W = 8, TILE_M = TILE_H * TILE_W;   // 128 pixels = UMMA M
 constexpr int THREADS = 128;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 
 struct ConvArgs {
     int B, H, W;
@@ -673,7 +673,7 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
     cudaError_t e;
     if (use_v1) {
         const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
-        int stages = pl.iters < MAX_STAGES ? pl.iters : MAX_STAGES;
+        int stages = pl.iters < 4 ? pl.iters : 4;
         while (stages > 1 && (size_t)stages * stage_bytes > 200 * 1024) --stages;
         a.stages = stages;
         const size_t smem = (size_t)stages * stage_bytes + 1024;
@@ -689,7 +689,8 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
         const int w_region = a.resident ? ((wbytes_all + 1023) & ~1023) : 0;
         const int a_bytes2 = (TILE_H + ks - 1) * box_w * row_bytes;
         const int stage_bytes = (a_bytes2 + (a.resident ? 0 : b_bytes) + 1023) & ~1023;
-        int stages = MAX_STAGES;
+        static const int stages_env = [] { const char* e = getenv("UAPS_CONV_STAGES"); return e ? atoi(e) : 4; }();
+        int stages = stages_env >= 2 && stages_env <= MAX_STAGES ? stages_env : 4;
         while (stages > 2 && (size_t)w_region + (size_t)stages * stage_bytes > 110 * 1024) --stages;
         if ((size_t)w_region + (size_t)stages * stage_bytes > 220 * 1024) stages = 2;
         while (stages > 1 && (size_t)w_region + (size_t)stages * stage_bytes > 220 * 1024) --stages;
