@@ -354,7 +354,7 @@ def run_ours(args):
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "exchange": None if world == 1 else ("nvlink peer-memory mailboxes, fused into the fold kernel"
                                                             if xchg is not None else "nccl all-reduce of the sums")},
-            "roofline": {"bound": "hbm", "kernel": "loss_pass2_kernel<4,4,4>", "achieved": ach2, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "loss_pass2_kernel<K=4,C=4,VEC=2,PF> (uaps_loss_pass2)", "achieved": ach2, "peak": peak,
                          "unit": "GB/s", "frac": ach2 / peak, "peak_source": peak_src,
                          "traffic": None if not traffic else traffic.get("pass2_dram_bytes_per_launch"),
                          "algorithmic_bytes_per_launch": bytes2,
