@@ -135,6 +135,8 @@ class FlatAdam:
 
 class UAPSTrainer:
     def __init__(self, model: torch.nn.Module, cfg: Optional[UAPSConfig] = None, group=None):
+        if group is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            group = dist.group.WORLD             # one process per GPU: the loss sums and the gradients span all ranks
         self.model, self.cfg, self.group = model, cfg or UAPSConfig(), group
         self.grads = FlatGradBuffer(model.parameters())
         if self.cfg.optimizer == "torch":
