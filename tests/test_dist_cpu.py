@@ -104,3 +104,18 @@ def test_single_process_allreduce_is_identity():
     from uaps_b200.losses import _allreduce_sums
     s = torch.arange(5, dtype=torch.float64)
     assert _allreduce_sums(s, None) == 1 and torch.equal(s, torch.arange(5, dtype=torch.float64))
+
+
+def test_flat_grad_buffer_layout():
+    """Every parameter's gradient slot starts on a 256-byte boundary (the kernels take 16-byte vector loads of biases
+    and BatchNorm parameters), the views alias the flat buffer, and padding stays zero under zero()."""
+    from uaps_b200.train import FlatGradBuffer
+    params = [torch.nn.Parameter(torch.randn(*s)) for s in [(16, 3, 3, 3), (16,), (2,), (4, 16, 3, 3), (7,)]]
+    buf = FlatGradBuffer(params)
+    assert buf.offsets == sorted(buf.offsets) and all(o % FlatGradBuffer.ALIGN == 0 for o in buf.offsets)
+    for p, off in zip(params, buf.offsets):
+        assert p.grad.shape == p.shape and p.grad.data_ptr() == buf.flat.data_ptr() + 4 * off
+        p.grad.fill_(1.0)
+    assert buf.flat.sum().item() == sum(p.numel() for p in params)      # padding untouched
+    buf.zero()
+    assert buf.flat.abs().sum().item() == 0.0
