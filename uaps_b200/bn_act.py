@@ -24,7 +24,8 @@ class _BnActFn(torch.autograd.Function):
         stats = torch.empty(2 * C, dtype=torch.float32, device=dev)          # save_mean | save_rstd
         out = torch.empty_like(y)
         lib = L.lib()
-        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        g32 = gamma.data if gamma.dtype == torch.float32 and gamma.is_contiguous() else gamma.detach().float().contiguous()
+        b32 = beta.data if beta.dtype == torch.float32 and beta.is_contiguous() else beta.detach().float().contiguous()
         with L.on_device(dev):
             L.check(lib.uaps_bn_stats_nhwc(y.data_ptr(), npix, C, sums.data_ptr(), sums[C:].data_ptr(), L.stream_ptr()),
                     "uaps_bn_stats_nhwc")

@@ -20,6 +20,7 @@ class StepContext:
         self.used = 0
         self.counters = []
         self.direct_grads = True
+        self.stream = None                 # raw cudaStream_t of the iteration, cached for the ~1150 launches (see _lib.stream_ptr)
 
     def take(self, n: int) -> torch.Tensor:
         """n zeroed doubles (falls back to a fresh tensor when the arena is exhausted)."""
@@ -32,6 +33,8 @@ class StepContext:
     def __enter__(self):
         global _active
         self._prev, _active = _active, self
+        if torch.cuda.is_available():
+            self.stream = torch.cuda.current_stream(self.device).cuda_stream
         return self
 
     def __exit__(self, *exc):
