@@ -291,6 +291,29 @@ def golden_unet(ref_unet):
     print(f"  UNet_UAPS forward/backward (B={B}, {H}x{W}): pinned, 334 state tensors")
 
 
+def golden_metrics():
+    """utilities/metrics.py:7-61 (pixel_accuracy, mIoU, mDice) evaluated by the reference's own functions on seeded
+    logits / masks, including an absent class (nanmean path), exact logit ties (argmax tie-break) and C != 4."""
+    import utilities.metrics as ref_metrics
+    out = {}
+    for name, (C, B, H, W, drop) in {"c4": (4, 4, 64, 64, None), "c2": (2, 3, 32, 48, None), "c4_absent2": (4, 2, 64, 64, 2),
+                                     "c7_absent5": (7, 2, 33, 35, 5)}.items():
+        g = torch.Generator().manual_seed(100 + C + H)
+        logits = torch.randn(B, C, H, W, generator=g) * 2
+        mask = torch.randint(0, C, (B, H, W), generator=g)
+        if drop is not None:
+            mask[mask == drop] = 0
+        logits[:, 1] = torch.where(torch.rand(B, H, W, generator=g) < 0.1, logits[:, 0], logits[:, 1])     # exact ties
+        out[name + "/logits"] = logits.numpy()
+        out[name + "/mask"] = mask.numpy()
+        out[name + "/n_classes"] = np.array(C)
+        out[name + "/pixel_accuracy"] = np.array(ref_metrics.pixel_accuracy(logits, mask), dtype=np.float64)
+        out[name + "/mIoU"] = np.array(ref_metrics.mIoU(logits, mask, n_classes=C), dtype=np.float64)
+        out[name + "/mDice"] = np.array(ref_metrics.mDice(logits, mask, n_classes=C), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+    print(f"  metrics (pixel_accuracy / mIoU / mDice): {len(out) // 6} cases from the reference's functions")
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("make_golden needs /root/reference (build container only)")
@@ -302,6 +325,7 @@ def main():
     golden_perturb(ref_unet)
     golden_losses(ref_losses)
     golden_unet(ref_unet)
+    golden_metrics()
     print("fixtures written to", OUT)
 
 

@@ -69,3 +69,19 @@ def test_predict_fast_path_and_checkpoint_roundtrip(tmp_path):
     load_checkpoint(path, m16, map_location=dev)
     p16 = m16.predict(x)
     assert p16.shape == full.shape and ((p16 - full).norm() / full.norm()).item() < 0.1
+
+
+def test_metrics_match_reference_golden():
+    """tests/golden/metrics.npz holds the outputs of the reference's OWN utilities/metrics.py functions
+    (oracle/make_golden.py:golden_metrics) -- the on-device confusion-matrix metrics must reproduce them."""
+    from conftest import load_cases
+    from uaps_b200 import metrics as M
+    dev = torch.device("cuda:0")
+    for name, c in load_cases("metrics.npz").items():
+        logits, mask, C = torch.from_numpy(c["logits"]).to(dev), torch.from_numpy(c["mask"]).to(dev), int(c["n_classes"])
+        assert M.pixel_accuracy(logits, mask) == pytest.approx(float(c["pixel_accuracy"]), rel=1e-12), name
+        assert M.mIoU(logits, mask, n_classes=C) == pytest.approx(float(c["mIoU"]), rel=1e-9), name
+        assert M.mDice(logits, mask, n_classes=C) == pytest.approx(float(c["mDice"]), rel=1e-9), name
+        acc = M.MetricAccumulator(dev)                    # per-batch means, as the reference's loop averages them
+        acc.update(logits, mask)
+        assert acc.result()["mDice"] == pytest.approx(float(c["mDice"]), rel=1e-9), name

@@ -139,3 +139,25 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_metric_restatement_matches_reference_golden():
+    """The loops of utilities/metrics.py:7-61 as restated for the GPU parity tests, against the outputs of the
+    reference's own functions (tests/golden/metrics.npz, written by oracle/make_golden.py:golden_metrics)."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from conftest import load_cases
+    for name, c in load_cases("metrics.npz").items():
+        logits, m, C = torch.from_numpy(c["logits"]), torch.from_numpy(c["mask"]).view(-1), int(c["n_classes"])
+        pred = torch.argmax(F.softmax(logits, dim=1), dim=1).view(-1)
+        assert float(torch.eq(pred, m).sum()) / m.numel() == float(c["pixel_accuracy"]), name
+        ious, dices = [], []
+        for k in range(1, C):
+            tc, tl = pred == k, m == k
+            if tl.sum().item() == 0:
+                ious.append(np.nan); dices.append(np.nan)
+                continue
+            inter, union = (tc & tl).sum().item(), (tc | tl).sum().item()
+            ious.append((inter + 1e-10) / (union + 1e-10)); dices.append(2 * (inter + 1e-10) / (union + inter + 1e-10))
+        assert np.nanmean(ious) == float(c["mIoU"]) and np.nanmean(dices) == float(c["mDice"]), name
