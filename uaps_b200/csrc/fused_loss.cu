@@ -149,8 +149,12 @@ __global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const
     }
     if (threadIdx.x < S) {
         const double* mine = reinterpret_cast<const double*>(x.box[x.rank]) + (size_t)ph * XCHG_WMAX * XCHG_SLOT + threadIdx.x;
+        double v[XCHG_WMAX];
+#pragma unroll
+        for (int p = 0; p < XCHG_WMAX; ++p) v[p] = p < x.world ? __ldcg(mine + (size_t)p * XCHG_SLOT) : 0.0;   // all loads in flight
         double r = 0.0;
-        for (int p = 0; p < x.world; ++p) r += __ldcg(mine + (size_t)p * XCHG_SLOT);     // rank order: identical on all ranks
+#pragma unroll
+        for (int p = 0; p < XCHG_WMAX; ++p) r += v[p];                                   // rank order: identical on all ranks
         s_sums[threadIdx.x] = r;
         sums[threadIdx.x] = r;
     }
