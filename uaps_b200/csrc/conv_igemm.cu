@@ -23,9 +23,12 @@
 //   D.  128 lanes x N_TILE fp32 columns of TMEM.  Epilogue: tcgen05.ld 32x32b, + bias, -> bf16 NHWC
 //   (or fp32 NCHW for the logits that feed the fused loss kernel).
 //
-// One output tile per CTA, 4 warps: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer
-// (warp 1 owns the TMEM allocation), all four warps = epilogue.  Small layers hide latency by many
-// co-resident CTAs (their stages are a few KB), big layers by the STAGES-deep ring inside the CTA.
+// Kernels.  conv_igemm_persistent_kernel (default): one CTA per SM slot (up to 6 per SM for the small layers) walks the
+// output tiles with stride gridDim.x; 6 warps: warp 0 lane 0 = TMA producer running ahead through a 2-4 stage mbarrier
+// ring, warp 1 lane 0 = MMA issuer alternating between two TMEM accumulators, warps 2-5 = epilogue (tcgen05.ld -> + bias
+// [-> LeakyReLU] -> bf16 NHWC / fp32 NCHW), so tile i's epilogue overlaps tile i+1's MMAs.  Layers whose packed weights fit
+// 80 KB keep them resident in shared memory and load ONE x-halo activation box per channel chunk for all nine taps.
+// conv_igemm_kernel (UAPS_CONV_V1=1): the first, one-tile-per-CTA version, kept for A/B profiling.
 #include <cstdlib>
 #include "tc_common.cuh"
 

@@ -11,8 +11,15 @@
 //       their accumulator lanes are never read).  8-pixel K atoms are one image row (10 pixels) apart (SBO).
 //   B = dY tile [128 px][min(Cout,64) ch] (x 2 boxes for Cout > 64): N-major, N = Cout of this CTA (<= 128).
 // Putting Cout on N and the taps on M makes the tensor time 12 * Cout cycles per 128-pixel tile (192 for the
-// 16-channel layers) instead of 576+ with the roles swapped.  The 3 accumulators D_r (3 x Cout fp32 columns) stay
-// in TMEM across all pixel tiles of the CTA (split-K over CTAs), then are added to dW with fp32 reductions.
+// 16-channel layers) instead of 576+ with the roles swapped.  What then bounds the small-channel layers is the SS-mode
+// operand FETCH (every MMA reads all its M rows from shared memory), so:
+//   * M = 64 instead of 128 whenever taps x channel-chunk rows fit (3 x 16 = 48): half the A bytes per instruction;
+//   * for Cout <= 64 the three VERTICAL taps ride in N as well ("fused_r"): with p' = p + (r-1, 0),
+//         dW[r][s][ci][co] = sum_p' X[p' + (0, s-1)][ci] * dY[p' - (r-1, 0)][co],
+//     the X box keeps only its column halo, the dY box gets a row halo, and N group g = 2 - r of the N-major dY descriptor is
+//     the dY tile shifted by g rows (LBO = one box row): one MMA per 16-pixel k-step (N = 3 * Cout) instead of three.
+// The accumulators (ks x Cout fp32 columns) stay in TMEM across all pixel tiles of the CTA (split-K over CTAs), then are
+// added to dW with fp32 reductions.  The TMA -> MMA ring is 8 / 6 / 3 stages deep for 16 / 32 / wider channel chunks.
 #include <cstdlib>
 #include "tc_common.cuh"
 
