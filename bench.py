@@ -5,9 +5,10 @@
 
 Headline workload (BASELINE.json configs[1], the shape of configs[2]'s unlabeled batch): the fused
 pseudo-label + KL-uncertainty + weighted CE/Dice loss, forward + backward, K=4 decoders, C=4
-classes, 64 x 256x256 pixels per GPU (268 MB of fp32 logits, > the 126 MB L2).  One "step" = pass1 +
-finalize + pass2 over one batch.  metric = pixels/s over all ranks (weak scaling: every rank has its
-own batch; the <=70-double partial-sum vector is all-reduced between the passes).
+classes, 64 x 256x256 pixels per GPU (268 MB of fp32 logits, > the 126 MB L2).  One "step" = pass 1 +
+fold/finalize + pass 2 over one batch (3 launches chained by programmatic dependent launch).  metric =
+pixels/s over all ranks (weak scaling: every rank has its own batch; the <=70-double partial-sum vector is
+exchanged between the passes inside the fold kernel, through NVLink peer-memory mailboxes).
 
   value     : logits resident in HBM, C-ABI calls timed with CUDA events on the launching stream.
   e2e       : the public API (uaps_unlabeled_loss + backward) fed from pinned HOST buffers, H2D copy
@@ -15,7 +16,9 @@ own batch; the <=70-double partial-sum vector is all-reduced between the passes)
   roofline  : the dominant kernel (pass 2: 8*K*C algorithmic bytes / pixel) against the measured HBM
               copy bandwidth in MEASURED_PEAKS.json; per-kernel numbers under "kernels".
   cpu_baseline : the oracle (restated reference expressions, torch CPU) on the box's host cores.
+  eager_cuda_baseline : the same expressions as torch-eager ops on the same GPU (the incumbent GPU path).
   train_step: secondary -- full UAPS iteration (two forwards, both losses, backward, Adam) iters/s.
+  inference : validation forward (BatchNorm folded, LeakyReLU in the conv epilogue), throughput and batch-1 latency.
 
 --impl reference times the reference's CPU implementation of the same path (the oracle port; the
 reference itself is pure Python over torch and its loss section is inline code that cannot be
