@@ -111,7 +111,8 @@ int uaps_loss_pass1_scalars(const float* const* z, int K, int B, int C, int64_t 
  * uaps_xchg_alloc -- the one allocation this library makes, because CUDA IPC needs the allocation base) and maps
  * every peer's mailbox through a 64-byte handle exchanged out of band (torch.distributed in uaps_b200/comm.py).
  * uaps_loss_pass1_exchange = pass 1, then ONE kernel that folds the partial sums, stores them into every rank's
- * mailbox over NVLink, waits for the world's sums and finalizes the scalars -- no NCCL call on the data path.
+ * mailbox over NVLink (8-byte words carrying 32 data bits + the epoch tag, so data and flag arrive together), collects
+ * the world's words from its own mailbox and finalizes the scalars -- no NCCL call on the data path.
  * mailboxes: host array of `world` device pointers as mapped in THIS process (own mailbox at [rank]);
  * epoch: 1, 2, 3, ... incremented by the caller per exchange, identical on all ranks; N_global: pixels of the
  * whole batch.  A peer that never arrives (UAPS_XCHG_TIMEOUT_MS, default 4000) turns the scalars into NaN and

@@ -63,7 +63,8 @@ class LossExchange:
         self.epoch = 0
 
     def next_epoch(self) -> int:
-        self.epoch = self.epoch % 0x7FFFFFFF + 1
+        # 1, 2, 3, ... as a 32-bit tag; the wrap skips 0 (the "never written" tag) and keeps the parity alternating
+        self.epoch = self.epoch + 1 if self.epoch < 0xFFFFFFFF else 2
         return self.epoch
 
     def status(self) -> int:

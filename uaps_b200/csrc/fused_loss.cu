@@ -80,9 +80,10 @@ int dispatch_k(int K, int C, int impl, bool sup, bool pass2, const LossArgs& a, 
 // exchange ahead: it cannot leave exchange e+1 before every peer has entered it).
 constexpr int XCHG_WMAX = UAPS_XCHG_MAX_RANKS;
 constexpr int XCHG_SLOT = 128;                                  // doubles per (phase, source) slot, >= sums_count max
-constexpr size_t XCHG_FLAGS_OFF = (size_t)2 * XCHG_WMAX * XCHG_SLOT * sizeof(double);
-constexpr int XCHG_FLAG_STRIDE = 32;                            // one flag per 128-byte line
-constexpr size_t XCHG_STATUS_OFF = XCHG_FLAGS_OFF + (size_t)2 * XCHG_WMAX * XCHG_FLAG_STRIDE * sizeof(unsigned);
+// Every double travels as TWO 8-byte words {32 data bits, epoch}: an aligned 8-byte store is delivered atomically, so
+// the flag arrives WITH the data (NCCL's "LL" idea) -- no fence + separate flag store + second NVLink hop.
+constexpr size_t XCHG_WORDS = (size_t)2 * XCHG_WMAX * 2 * XCHG_SLOT;          // [phase][source][2 * slot] x 8 bytes
+constexpr size_t XCHG_STATUS_OFF = XCHG_WORDS * sizeof(unsigned long long);
 constexpr size_t XCHG_BYTES = XCHG_STATUS_OFF + 128;
 static_assert(sums_count(KMAX, CMAX) <= XCHG_SLOT, "slot too small");
 
@@ -93,13 +94,11 @@ struct ExchangeArgs {
     unsigned long long timeout_ns;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_word_sys(unsigned long long* p, unsigned data, unsigned flag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(flag) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void ld_word_sys(const unsigned long long* p, unsigned& data, unsigned& flag) {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(data), "=r"(flag) : "l"(p) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
@@ -116,30 +115,33 @@ __global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const
     pdl_trigger();
     pdl_wait();
     cta_fold_rows(partials, S, nblocks, s_sums);                 // local fold, as loss_fold_finalize_kernel
+    __shared__ unsigned s_words[XCHG_WMAX][2 * XCHG_SLOT];
     const int ph = x.epoch & 1;
-    // scatter: my sums into slot [ph][rank] of every mailbox (peer stores travel over NVLink)
-    for (int t = threadIdx.x; t < x.world * S; t += blockDim.x) {
-        const int p = t / S, i = t - p * S;
-        double* dst = reinterpret_cast<double*>(x.box[p]) + ((size_t)(ph * XCHG_WMAX + x.rank) * XCHG_SLOT + i);
-        __stcg(dst, s_sums[i]);
+    const int nw = 2 * S;                                        // 32-bit halves of my S doubles
+    // scatter: word idx of my sums -> slot [ph][rank][idx] of EVERY mailbox (peer stores travel over NVLink), tagged with the epoch
+    for (int t = threadIdx.x; t < x.world * nw; t += blockDim.x) {
+        const int p = t / nw, idx = t - p * nw;
+        const unsigned bits = reinterpret_cast<const unsigned*>(s_sums)[idx];
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(x.box[p]) +
+                                  ((size_t)(ph * XCHG_WMAX + x.rank) * 2 * XCHG_SLOT + idx);
+        st_word_sys(dst, bits, x.epoch);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < x.world) {
-        unsigned* f = reinterpret_cast<unsigned*>(x.box[threadIdx.x] + XCHG_FLAGS_OFF) + (ph * XCHG_WMAX + x.rank) * XCHG_FLAG_STRIDE;
-        st_release_sys(f, x.epoch);
-    }
-    // gather: wait until every source's flag in MY mailbox reached this epoch (bounded spin: a dead peer must not
-    // hang the GPU -- on timeout the scalars become NaN and the status word records the epoch)
+    // gather: every word of every source in MY mailbox, as soon as its tag shows this epoch (the other phase's words
+    // carry epoch - 1, this phase's stale ones epoch - 2).  Bounded spin: a dead peer must not hang the GPU -- on timeout
+    // the scalars become NaN and the status word records the epoch.
     int timed_out = 0;
-    if (threadIdx.x < x.world) {
-        const unsigned* f = reinterpret_cast<const unsigned*>(x.box[x.rank] + XCHG_FLAGS_OFF) +
-                            (ph * XCHG_WMAX + threadIdx.x) * XCHG_FLAG_STRIDE;
+    for (int t = threadIdx.x; t < x.world * nw; t += blockDim.x) {
+        const int p = t / nw, idx = t - p * nw;
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(x.box[x.rank]) +
+                                        ((size_t)(ph * XCHG_WMAX + p) * 2 * XCHG_SLOT + idx);
+        unsigned data, flag;
         const unsigned long long t0 = global_timer_ns();
-        while ((int)(ld_acquire_sys(f) - x.epoch) < 0) {
+        for (;;) {
+            ld_word_sys(src, data, flag);
+            if (flag == x.epoch) break;
             if (global_timer_ns() - t0 > x.timeout_ns) { timed_out = 1; break; }
-            __nanosleep(64);
         }
+        s_words[p][idx] = data;
     }
     timed_out = __syncthreads_or(timed_out);
     if (timed_out) {
@@ -148,13 +150,9 @@ __global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const
         return;
     }
     if (threadIdx.x < S) {
-        const double* mine = reinterpret_cast<const double*>(x.box[x.rank]) + (size_t)ph * XCHG_WMAX * XCHG_SLOT + threadIdx.x;
-        double v[XCHG_WMAX];
-#pragma unroll
-        for (int p = 0; p < XCHG_WMAX; ++p) v[p] = p < x.world ? __ldcg(mine + (size_t)p * XCHG_SLOT) : 0.0;   // all loads in flight
         double r = 0.0;
-#pragma unroll
-        for (int p = 0; p < XCHG_WMAX; ++p) r += v[p];                                   // rank order: identical on all ranks
+        for (int p = 0; p < x.world; ++p)                        // rank order: identical on all ranks
+            r += __hiloint2double((int)s_words[p][2 * threadIdx.x + 1], (int)s_words[p][2 * threadIdx.x]);
         s_sums[threadIdx.x] = r;
         sums[threadIdx.x] = r;
     }
