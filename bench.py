@@ -249,17 +249,17 @@ def run_ours(args):
         # ev = (after pass 1 + fold/finalize [+ all-reduce], after pass 2); the step starts where the previous one ended
         if world == 1:          # single rank: fold + finalize fused into one launch behind pass 1
             L.check(lib.uaps_loss_pass1_scalars(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0,
-                                                CW1, CW2, sc.data_ptr(), st), "pass1")
+                                                CW1, CW2, sc.data_ptr(), None, st), "pass1")
         elif xchg is not None:  # fold + peer-memory exchange + finalize in one launch
             L.check(lib.uaps_loss_pass1_exchange(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0,
-                                                 xchg.ptrs, rank, world, xchg.next_epoch(), N * world, CW1, CW2, sc.data_ptr(), st),
+                                                 xchg.ptrs, rank, world, xchg.next_epoch(), N * world, CW1, CW2, sc.data_ptr(), None, None, st),
                     "pass1")
         else:
             L.check(lib.uaps_loss_pass1(zp, K, B, C, H * W, w_arr, None, ws.data_ptr(), sums.data_ptr(), None, None, 0, st), "pass1")
             dist.all_reduce(sums, group=group)
             L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, N * world, CW1, CW2, 0, sc.data_ptr(), st), "finalize")
         if ev: ev[0].record()
-        L.check(lib.uaps_loss_pass2(zp, K, B, C, H * W, w_arr, None, sc.data_ptr(), go.data_ptr(), dzp, 0, st), "pass2")
+        L.check(lib.uaps_loss_pass2(zp, K, B, C, H * W, w_arr, None, sc.data_ptr(), go.data_ptr(), dzp, 0, None, st), "pass2")
         if ev: ev[1].record()
 
     def barrier():
@@ -412,8 +412,8 @@ def loss_sweep(dev, lib, L, iters: int = 10):
 
         def step():
             L.check(lib.uaps_loss_pass1_scalars(zp, k, b, c, h * w, wa, None, ws.data_ptr(), sums.data_ptr(), None, None, 0,
-                                                CW1, CW2, sc.data_ptr(), st), "p1")
-            L.check(lib.uaps_loss_pass2(zp, k, b, c, h * w, wa, None, sc.data_ptr(), go.data_ptr(), dzp, 0, st), "p2")
+                                                CW1, CW2, sc.data_ptr(), None, st), "p1")
+            L.check(lib.uaps_loss_pass2(zp, k, b, c, h * w, wa, None, sc.data_ptr(), go.data_ptr(), dzp, 0, None, st), "p2")
         for _ in range(3):
             step()
         torch.cuda.synchronize()

@@ -29,7 +29,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define UAPS_ABI_VERSION 1
+#define UAPS_ABI_VERSION 2
 #define UAPS_KMAX 6              /* decoders: reference uses 4 (UAPS_unet.py:219-222); ablation up to 5 */
 #define UAPS_CMAX 8              /* classes: 4 NEU, 2 KoSDD2, 7 DAGM (DAGM-Dataset-codes/UAPS_model.py:11) */
 
@@ -43,6 +43,45 @@ enum {
 
 int         uaps_abi_version(void);
 const char* uaps_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident per-iteration state.  The reference's loop draws its per-iteration scalars on the HOST
+ * (np.random.dirichlet :251, np.random.uniform UAPS_unet.py:165, the ramp :279-280, Adam's step count) and
+ * passes them to kernels by value; that forces ~1150 launches per iteration through Python.  Here they live in
+ * one small device struct advanced by ONE single-thread kernel (uaps_step_begin) at the top of the iteration,
+ * and every entry point below that used to take such a scalar also takes a nullable device pointer into this
+ * struct, so a whole iteration (two forwards, both losses, backward, optimizer) is a static launch sequence
+ * that can be captured once into a CUDA graph and replayed.
+ * ------------------------------------------------------------------------------------------- */
+#define UAPS_STEP_USLOTS 16
+typedef struct UapsStepState {
+    uint64_t iter;              /* completed iterations; the ramp "epoch" is iter / iters_per_ramp_epoch (:279-280) */
+    uint64_t key_rank;          /* Philox key offset of this iteration for per-rank draws (dropout masks, feature noise) */
+    uint64_t key_shared;        /* the same for draws every rank must agree on                                       */
+    uint64_t adam_step;         /* optimizer steps taken (bias correction)                                            */
+    uint32_t xchg_base;         /* exchange epochs of this iteration are xchg_base + 1 .. xchg_base + n_exchanges      */
+    uint32_t xchg_next;
+    uint32_t skipped;           /* written by uaps_adam_step: 1 = the loss was not finite, the update was skipped      */
+    uint32_t n_skipped;         /* how often that happened (latched, never reset by the library)                       */
+    float lr;                   /* HOST-written learning rate (a scheduler edits it, :113); read by uaps_step_begin     */
+    float adam_step_size;       /* lr / (1 - beta1^t)                                                                  */
+    float adam_inv_bc2_sqrt;    /* 1 / sqrt(1 - beta2^t)                                                               */
+    float reserved;
+    float mix_w[8];             /* Dirichlet(1,...,1) draw over the K decoders (:251), fp32-rounded                    */
+    float cw1, cw2;             /* consistency_i * sigmoid_rampup(iter / iters_per_ramp_epoch, rampup_length)          */
+    float u[UAPS_STEP_USLOTS];  /* FeatureDropout thresholds U(0.7, 0.9) (UAPS_unet.py:165), one per call of the step  */
+} UapsStepState;
+/* float offsets inside the `wcw` block (&state->mix_w[0]) the loss entry points take */
+#define UAPS_WCW_CW1 8
+#define UAPS_WCW_CW2 9
+
+/* Advance `state` (device, zero-initialised once, 16-byte aligned) by one iteration: draws mix_w (K weights), the
+ * n_u thresholds and the two Philox keys from Philox4x32-10 keyed by (seed_shared | seed_rank, iter), evaluates the
+ * ramp in fp64 (utilities/ramps.py:19-26), Adam's bias corrections for step adam_step + 1 (not advanced when the
+ * previous update was skipped), moves the exchange-epoch window by n_exchanges, and increments iter. */
+int uaps_step_begin(UapsStepState* state, uint64_t seed_rank, uint64_t seed_shared, int K, int n_u,
+                    double consistency1, double consistency2, double rampup_length, int iters_per_ramp_epoch,
+                    int n_exchanges, float beta1, float beta2, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused pseudo-label + KL-uncertainty + uncertainty-weighted CE/Dice loss
@@ -104,7 +143,9 @@ int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t HW,
 int uaps_loss_pass1_scalars(const float* const* z, int K, int B, int C, int64_t HW,
                             const float* mix_w, const int64_t* labels, void* workspace, double* sums,
                             int64_t* pseudo_out, float* const* exp_var_out, int flags,
-                            float cw1, float cw2, float* scalars, cudaStream_t stream);
+                            float cw1, float cw2, float* scalars,
+                            const float* wcw_dev, /* nullable: &UapsStepState.mix_w[0]; then mix_w / cw1 / cw2 are read from the device */
+                            cudaStream_t stream);
 
 /* ---- multi-GPU exchange (replaces the DataParallel gather of UAPS_model.py:13 for the loss sums) ----------
  * One process per GPU, all on one NVLink/NVSwitch domain.  Each rank owns a MAILBOX (device memory allocated by
@@ -129,7 +170,10 @@ int uaps_loss_pass1_exchange(const float* const* z, int K, int B, int C, int64_t
                              const float* mix_w, const int64_t* labels, void* workspace, double* sums,
                              int64_t* pseudo_out, float* const* exp_var_out, int flags,
                              void* const* mailboxes, int rank, int world, unsigned epoch, int64_t N_global,
-                             float cw1, float cw2, float* scalars, cudaStream_t stream);
+                             float cw1, float cw2, float* scalars,
+                             const float* wcw_dev,        /* nullable, as above */
+                             const uint32_t* epoch_dev,   /* nullable: &UapsStepState.xchg_base; the epoch used is *epoch_dev + epoch */
+                             cudaStream_t stream);
 
 /* sums_global: device, uaps_loss_sums_count doubles (all-reduced over ranks by the caller when
  * the batch is sharded); N_global = total pixels behind those sums.  supervised != 0 selects
@@ -144,7 +188,7 @@ int uaps_loss_finalize(const double* sums_global, int K, int C, int64_t N_global
 int uaps_loss_pass2(const float* const* z, int K, int B, int C, int64_t HW,
                     const float* mix_w, const int64_t* labels,
                     const float* scalars, const float* grad_out,
-                    float* const* dz, int flags, cudaStream_t stream);
+                    float* const* dz, int flags, const float* wcw_dev /* nullable, as in pass 1 */, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Encoder-feature perturbations (utilities/UAPS_unet.py:156-185, applied at :227-231).
@@ -197,11 +241,13 @@ int uaps_fdrop_stats_nhwc(const void* x, int B, int C, int64_t HW, float* attent
 int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range, double p_drop,
                        const float* attention, const uint32_t* smax_enc, float u,
                        void* y_noise, void* y_drop, void* y_fdrop, int B, int C, int64_t HW,
+                       const uint64_t* seed_dev, /* nullable: *seed_dev is added to seed (&UapsStepState.key_rank) */
+                       const float* u_dev,       /* nullable: overrides u (&UapsStepState.u[slot]) */
                        cudaStream_t stream);
 int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, const void* g_fdrop, uint64_t seed,
                            float noise_range, double p_drop, const float* attention,
                            const uint32_t* smax_enc, float u, void* dx, int B, int C, int64_t HW,
-                           cudaStream_t stream);
+                           const uint64_t* seed_dev, const float* u_dev, cudaStream_t stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (utilities/UAPS_unet.py:74-75) and
  * nn.MaxPool2d(2) (:56) on channels-last bf16, C % 8 == 0.
@@ -228,12 +274,13 @@ int uaps_bn_stats_nhwc(const void* y, int64_t npix, int C, double* sum, double* 
 int uaps_bn_act_nhwc(const void* y, const double* sum, const double* sumsq, const float* gamma,
                      const float* beta, float* running_mean, float* running_var, float momentum,
                      float eps, float slope, double p_drop, uint64_t seed, void* out,
-                     float* save_mean, float* save_rstd, int64_t npix, int C, cudaStream_t stream);
+                     float* save_mean, float* save_rstd, int64_t npix, int C,
+                     const uint64_t* seed_dev /* nullable: *seed_dev is added to seed */, cudaStream_t stream);
 int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float* gamma, const float* beta,
                          const float* save_mean, const float* save_rstd, float slope, double p_drop,
                          uint64_t seed, double* sum_g, double* sum_gx, void* dy,
                          float* dgamma_accum, float* dbeta_accum, /* nullable pair: fp32 [C], += d gamma / d beta */
-                         int64_t npix, int C, cudaStream_t stream);
+                         int64_t npix, int C, const uint64_t* seed_dev, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 / TMEM / TMA (3x3 pad 1 or 1x1, stride 1), bf16 operands, fp32
@@ -285,7 +332,11 @@ int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int x_c_stri
  *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps).
  * step = 1, 2, 3, ...; grad_scale multiplies g first (1 when the gradient is already that of the global loss). */
 int uaps_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t step, float lr, float beta1,
-                   float beta2, float eps, float grad_scale, cudaStream_t stream);
+                   float beta2, float eps, float grad_scale,
+                   UapsStepState* state,   /* nullable: step size / bias correction come from the device state (step, lr ignored) */
+                   const float* guard,     /* nullable device float (the iteration's loss): if it is not finite the update is
+                                              skipped and state->skipped / n_skipped record it (needs state) */
+                   cudaStream_t stream);
 
 /* On-device confusion matrix behind utilities/metrics.py (pixel_accuracy :8, mIoU :16, mDice :40):
  * conf[label * C + argmax(softmax(logits))] += 1 per pixel (labels outside [0,C) ignored).  logits [B,C,HW] fp32,

@@ -35,7 +35,7 @@ def _single(L, lib, z, labels=None):
     sc = torch.empty(lib.uaps_loss_scalars_count(K, CC), dtype=torch.float32, device=dev)
     L.check(lib.uaps_loss_pass1_scalars(L.ptr_array(z), K, z[0].shape[0], CC, H * W, L.float_array(MIX),
                                         None if labels is None else labels.data_ptr(), ws.data_ptr(), sums.data_ptr(),
-                                        None, None, 0, CW1, CW2, sc.data_ptr(), L.stream_ptr()), "single")
+                                        None, None, 0, CW1, CW2, sc.data_ptr(), None, L.stream_ptr()), "single")
     torch.cuda.synchronize()
     return sc, sums
 
@@ -69,7 +69,7 @@ def test_two_ranks_on_one_device(supervised):
                     L.check(lib.uaps_loss_pass1_exchange(L.ptr_array(zs[r]), K, shard, CC, H * W, L.float_array(MIX),
                                                          None if ls[r] is None else ls[r].data_ptr(), ws[r].data_ptr(),
                                                          sums[r].data_ptr(), None, None, 0, boxes, r, world, epoch, B * H * W,
-                                                         CW1, CW2, sc[r].data_ptr(), streams[r].cuda_stream), "exchange")
+                                                         CW1, CW2, sc[r].data_ptr(), None, None, streams[r].cuda_stream), "exchange")
             torch.cuda.synchronize()
             assert torch.equal(sc[0], sc[1]), "ranks must finalize bit-identical scalars"
             assert torch.equal(sums[0], sums[1])
@@ -102,7 +102,7 @@ def test_missing_peer_times_out_instead_of_hanging(monkeypatch):
     try:
         L.check(lib.uaps_loss_pass1_exchange(L.ptr_array(z), K, B, CC, H * W, L.float_array(MIX), None, ws.data_ptr(),
                                              sums.data_ptr(), None, None, 0, boxes, 0, 2, 1, 2 * B * H * W, CW1, CW2,
-                                             sc.data_ptr(), L.stream_ptr()), "exchange")     # rank 1 never shows up
+                                             sc.data_ptr(), None, None, L.stream_ptr()), "exchange")     # rank 1 never shows up
         torch.cuda.synchronize()
         assert torch.isnan(sc).all()
         out = C.c_uint(0)
@@ -124,7 +124,7 @@ def test_invalid_exchange_arguments():
     boxes = (C.c_void_p * 2)()
     args = lambda world, rank, epoch, b=boxes: (L.ptr_array(z), K, B, CC, H * W, L.float_array(MIX), None, ws.data_ptr(),
                                                 sums.data_ptr(), None, None, 0, b, rank, world, epoch, B * H * W, CW1, CW2,
-                                                sc.data_ptr(), L.stream_ptr())
+                                                sc.data_ptr(), None, None, L.stream_ptr())
     assert lib.uaps_loss_pass1_exchange(*args(2, 0, 1)) != 0          # null mailboxes
     assert lib.uaps_loss_pass1_exchange(*args(9, 0, 1)) != 0          # too many ranks
     assert lib.uaps_loss_pass1_exchange(*args(2, 2, 1)) != 0          # rank out of range

@@ -51,7 +51,7 @@ def test_predict_fast_path_and_checkpoint_roundtrip(tmp_path):
     from uaps_b200.unet import UNet_UAPS, load_checkpoint, save_checkpoint
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    m = UNet_UAPS(3, 4).to(dev).eval()
+    m = UNet_UAPS(3, 4, compute="fp32").to(dev).eval()
     x = torch.randn(2, 3, 64, 64, device=dev)
     with torch.no_grad():
         full = m(x)[0]
@@ -62,7 +62,7 @@ def test_predict_fast_path_and_checkpoint_roundtrip(tmp_path):
     ck = torch.load(path, map_location="cpu")
     assert set(ck) == {"epoch", "best_dice_1", "state_dict", "optimizer"}
     assert all(k.startswith("module.") for k in ck["state_dict"]) and len(ck["state_dict"]) == 334
-    m2 = UNet_UAPS(3, 4).to(dev).eval()
+    m2 = UNet_UAPS(3, 4, compute="fp32").to(dev).eval()
     assert load_checkpoint(path, m2, map_location=dev) == (7, 0.85)
     assert torch.equal(m2.predict(x), m.predict(x))
     m16 = UNet_UAPS(3, 4, compute="bf16").to(dev).eval()

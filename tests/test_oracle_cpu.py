@@ -116,7 +116,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), f"{name} declared in include/uaps_b200.h but not exported"
     assert sorted(_lib.exported_symbols()) == declared, "python binding and header diverge"
     lib = _lib.lib()
-    assert lib.uaps_abi_version() == 1
+    assert lib.uaps_abi_version() == _lib.ABI_VERSION == 2
     # pure host-side queries (no GPU work)
     assert lib.uaps_loss_sums_count(4, 4) == 3 * 4 + 2 * 16 + 4
     assert lib.uaps_loss_scalars_count(4, 4) == 8 + 16 + 32

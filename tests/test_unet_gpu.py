@@ -23,7 +23,7 @@ def test_state_dict_keys_and_golden_forward_backward():
     torch.backends.cuda.matmul.allow_tf32 = False
     g = np.load(os.path.join(GOLDEN, "unet_small.npz"))
     sd = synthetic_state_dict(3, 4)
-    model = UNet_UAPS(3, 4)
+    model = UNet_UAPS(3, 4, compute="fp32")
     assert list(model.state_dict().keys()) != [] and set(model.state_dict().keys()) == set(sd.keys())
     assert len(model.state_dict()) == 334
     load_reference_state_dict(model, {"module." + k: v for k, v in sd.items()})     # DataParallel-style keys
@@ -66,7 +66,7 @@ def test_against_oracle_on_device_neu_shape():
     dev = torch.device("cuda:0")
     torch.backends.cudnn.allow_tf32 = False
     sd = synthetic_state_dict(3, 4, seed=7)
-    model = UNet_UAPS(3, 4)
+    model = UNet_UAPS(3, 4, compute="fp32")
     model.load_state_dict(sd)
     model = model.to(dev).train()
     x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(0)).to(dev)
@@ -83,7 +83,7 @@ def test_net_factory_and_input_check():
     from uaps_b200.unet import net_factory
     assert net_factory("unet_ccps") is None            # the reference returns None for unknown names
     m = net_factory("unet_uaps", in_chns=1, class_num=2)
-    assert next(m.parameters()).is_cuda
+    assert next(m.parameters()).is_cuda and m.compute == "bf16"      # the drop-in default is the hand-written path
     with pytest.raises(RuntimeError):
         m(torch.randn(1, 1, 200, 200, device="cuda"))   # 200 is not a multiple of 16 (reference fails in cat)
     out = m(torch.randn(2, 1, 64, 96, device="cuda"))
@@ -110,7 +110,7 @@ def test_bf16_tcgen05_path():
     dev = torch.device("cuda:0")
     torch.backends.cudnn.allow_tf32 = False
     sd = synthetic_state_dict(3, 4, seed=3)
-    m32, m16, mref = UNet_UAPS(3, 4), UNet_UAPS(3, 4, compute="bf16"), UNet_UAPS(3, 4, compute="bf16")
+    m32, m16, mref = UNet_UAPS(3, 4, compute="fp32"), UNet_UAPS(3, 4, compute="bf16"), UNet_UAPS(3, 4, compute="bf16")
     for m in (m32, m16, mref):
         m.load_state_dict(sd)
         m.to(dev).train()

@@ -19,7 +19,7 @@ def run(K, C, B, H, W, flags=0, iters=10):
     N = B * H * W
     def p1(): L.check(lib.uaps_loss_pass1(zp, K, B, C, H * W, w, None, ws.data_ptr(), sums.data_ptr(), None, None, flags, st), "p1")
     def fin(): L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, N, 0.1, 0.1, 0, sc.data_ptr(), st), "fin")
-    def p2(): L.check(lib.uaps_loss_pass2(zp, K, B, C, H * W, w, None, sc.data_ptr(), go.data_ptr(), dzp, flags, st), "p2")
+    def p2(): L.check(lib.uaps_loss_pass2(zp, K, B, C, H * W, w, None, sc.data_ptr(), go.data_ptr(), dzp, flags, None, st), "p2")
     for _ in range(3): p1(); fin(); p2()
     torch.cuda.synchronize()
     res = {}

@@ -23,6 +23,16 @@ LOSS_EXACT = 1
 SC_LOSS_U, SC_PS_LOSS, SC_L_UNCERT, SC_CW1, SC_CW2, SC_INV_N, SC_MEAN_CE, SC_MEAN_DICE, SC_BASE = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 _vp, _i, _i64, _u64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double
+ABI_VERSION = 2
+STEP_USLOTS = 16
+
+
+class StepStateStruct(C.Structure):
+    """Mirror of ``UapsStepState`` (include/uaps_b200.h): the device-resident per-iteration scalars."""
+    _fields_ = [("iter", C.c_uint64), ("key_rank", C.c_uint64), ("key_shared", C.c_uint64), ("adam_step", C.c_uint64),
+                ("xchg_base", C.c_uint32), ("xchg_next", C.c_uint32), ("skipped", C.c_uint32), ("n_skipped", C.c_uint32),
+                ("lr", C.c_float), ("adam_step_size", C.c_float), ("adam_inv_bc2_sqrt", C.c_float), ("reserved", C.c_float),
+                ("mix_w", C.c_float * 8), ("cw1", C.c_float), ("cw2", C.c_float), ("u", C.c_float * STEP_USLOTS)]
 
 _SIGNATURES = {
     "uaps_abi_version": (_i, []),
@@ -31,9 +41,10 @@ _SIGNATURES = {
     "uaps_loss_scalars_count": (_i, [_i, _i]),
     "uaps_loss_workspace_bytes": (C.c_size_t, [_i, _i]),
     "uaps_loss_pass1": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
-    "uaps_loss_pass1_scalars": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp]),
+    "uaps_step_begin": (_i, [_vp, _u64, _u64, _i, _i, _d, _d, _d, _i, _i, _f, _f, _vp]),
+    "uaps_loss_pass1_scalars": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "uaps_loss_pass1_exchange": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, C.c_uint, _i64,
-                                      _f, _f, _vp, _vp]),
+                                      _f, _f, _vp, _vp, _vp, _vp]),
     "uaps_xchg_mailbox_bytes": (C.c_size_t, []),
     "uaps_xchg_alloc": (_i, [_vp]),
     "uaps_xchg_free": (_i, [_vp]),
@@ -42,27 +53,27 @@ _SIGNATURES = {
     "uaps_xchg_close": (_i, [_vp]),
     "uaps_xchg_status": (_i, [_vp, _vp, _vp]),
     "uaps_loss_finalize": (_i, [_vp, _i, _i, _i64, _f, _f, _i, _vp, _vp]),
-    "uaps_loss_pass2": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "uaps_loss_pass2": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "uaps_feature_noise": (_i, [_vp, _vp, _u64, _f, _vp, _i, _i64, _vp]),
     "uaps_dropout": (_i, [_vp, _vp, _u64, _d, _vp, _i64, _vp]),
     "uaps_fdrop_stats": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp]),
     "uaps_fdrop_apply": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i64, _vp]),
     "uaps_perturb3": (_i, [_vp, _vp, _vp, _u64, _f, _d, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i64, _vp]),
     "uaps_fdrop_stats_nhwc": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp]),
-    "uaps_perturb3_nhwc": (_i, [_vp, _u64, _f, _d, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i64, _vp]),
-    "uaps_perturb3_nhwc_bwd": (_i, [_vp, _vp, _vp, _u64, _f, _d, _vp, _vp, _f, _vp, _i, _i, _i64, _vp]),
+    "uaps_perturb3_nhwc": (_i, [_vp, _u64, _f, _d, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]),
+    "uaps_perturb3_nhwc_bwd": (_i, [_vp, _vp, _vp, _u64, _f, _d, _vp, _vp, _f, _vp, _i, _i, _i64, _vp, _vp, _vp]),
     "uaps_upsample2x_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "uaps_maxpool2_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "uaps_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "uaps_bn_stats_nhwc": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
-    "uaps_bn_act_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _d, _u64, _vp, _vp, _vp, _i64, _i, _vp]),
-    "uaps_bn_act_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _d, _u64, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "uaps_bn_act_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _d, _u64, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "uaps_bn_act_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _d, _u64, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "uaps_conv_packed_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "uaps_conv_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "uaps_conv_fprop": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "uaps_conv_fprop_act": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _vp]),
     "uaps_conv_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "uaps_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _f, _vp]),
+    "uaps_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
     "uaps_confusion": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
     "uaps_perturb3_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _f, _d, _vp, _vp, _f, _vp, _i, _i, _i64, _vp]),
 }
@@ -86,7 +97,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the ABI and the binding diverge
             fn.restype, fn.argtypes = res, args
-        if handle.uaps_abi_version() != 1:
+        if handle.uaps_abi_version() != ABI_VERSION:
             raise RuntimeError("libuaps_b200.so ABI version mismatch")
         _lib = handle
     return _lib

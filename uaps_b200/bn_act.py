@@ -12,7 +12,7 @@ from .perturb import _next_seed
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, slope, p_drop, seed):
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, slope, p_drop, seed, seed_dev):
         L.require_cuda(y)
         if y.dtype != torch.bfloat16 or not y.is_contiguous(memory_format=torch.channels_last):
             raise RuntimeError("bn_act expects a channels_last bf16 [B,C,H,W] tensor")
@@ -33,16 +33,16 @@ class _BnActFn(torch.autograd.Function):
                                          None if running_mean is None else running_mean.data_ptr(),
                                          None if running_var is None else running_var.data_ptr(),
                                          momentum, eps, slope, p_drop, seed, out.data_ptr(), stats.data_ptr(),
-                                         stats[C:].data_ptr(), npix, C, L.stream_ptr()), "uaps_bn_act_nhwc")
+                                         stats[C:].data_ptr(), npix, C, seed_dev, L.stream_ptr()), "uaps_bn_act_nhwc")
         ctx.save_for_backward(y, g32, b32, stats)
-        ctx.cfg = (slope, p_drop, seed)
+        ctx.cfg = (slope, p_drop, seed, seed_dev)
         ctx.params = (gamma, beta)
         return out
 
     @staticmethod
     def backward(ctx, g):
         y, g32, b32, stats = ctx.saved_tensors
-        slope, p_drop, seed = ctx.cfg
+        slope, p_drop, seed, seed_dev = ctx.cfg
         B, C, H, W = y.shape
         g = g.contiguous(memory_format=torch.channels_last)
         if g.dtype != torch.bfloat16:
@@ -59,20 +59,25 @@ class _BnActFn(torch.autograd.Function):
                                                  sums[C:].data_ptr(), dy.data_ptr(),
                                                  gamma.grad.data_ptr() if direct else None,
                                                  beta.grad.data_ptr() if direct else None,
-                                                 B * H * W, C, L.stream_ptr()), "uaps_bn_act_bwd_nhwc")
+                                                 B * H * W, C, seed_dev, L.stream_ptr()), "uaps_bn_act_bwd_nhwc")
         if direct:                               # already added into gamma.grad / beta.grad by the kernel
-            return dy, None, None, None, None, None, None, None, None, None
-        return dy, sums[C:].float(), sums[:C].float(), None, None, None, None, None, None, None
+            return (dy,) + (None,) * 10
+        return (dy, sums[C:].float(), sums[:C].float()) + (None,) * 8
 
 
 def bn_lrelu_dropout(y: torch.Tensor, bn: torch.nn.BatchNorm2d, p_drop: float = 0.0, slope: float = 0.01,
                      seed=None) -> torch.Tensor:
     """dropout(leaky_relu(batch_norm(y))) with batch statistics; advances bn's running statistics like
     nn.BatchNorm2d in training mode."""
+    seed_dev = None
     if p_drop > 0.0 and seed is None:
-        seed = _next_seed()
+        sc = stepctx.current()
+        if sc is not None and sc.state is not None:       # device-resident step: per-call constant + the iteration's key
+            seed, seed_dev = sc.next_seed(), sc.state.ptr("key_rank")
+        else:
+            seed = _next_seed()
     out = _BnActFn.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum), float(bn.eps),
-                         float(slope), float(p_drop), 0 if seed is None else int(seed))
+                         float(slope), float(p_drop), 0 if seed is None else int(seed), seed_dev)
     if bn.num_batches_tracked is not None:
         sc = stepctx.current()
         if sc is not None:

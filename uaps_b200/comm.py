@@ -87,46 +87,59 @@ class LossExchange:
 
 
 _exchanges: Dict[tuple, Optional[LossExchange]] = {}
+_owned = []
+
+
+def new_exchange(group, device: torch.device) -> Optional[LossExchange]:
+    """A fresh exchange (own mailboxes, epochs starting at 0) for (group, device), or None when the group cannot use
+    peer memory (not NCCL, ranks on several hosts, more than 8 ranks, UAPS_LOSS_EXCHANGE=nccl, or the mapping failed on
+    any rank).  COLLECTIVE: every rank of the group must call it, and every rank gets the same kind of answer.
+    ``UAPSTrainer`` takes one per trainer: its exchange epochs are counted on the device (UapsStepState.xchg_base), so
+    they must not share mailboxes with the host-counted epochs of direct ``uaps_unlabeled_loss(group=...)`` calls."""
+    if not dist.is_initialized():
+        return None
+    ok = (os.environ.get("UAPS_LOSS_EXCHANGE", "peer") != "nccl" and dist.get_backend(group) == "nccl"
+          and 1 < dist.get_world_size(group) <= MAX_RANKS)
+    if ok:                                   # collective decision: every rank must take the same branch
+        hosts = [None] * dist.get_world_size(group)
+        dist.all_gather_object(hosts, socket.gethostname(), group=group)
+        ok = len(set(hosts)) == 1
+    if not ok:
+        return None
+    # mapping a peer's mailbox can fail (no P2P path, IPC disabled in the container ...): every rank must then
+    # take the NCCL route, so the outcome is agreed on collectively before anybody uses the exchange
+    xchg, err = None, None
+    try:
+        xchg = LossExchange(group, device)
+    except Exception as e:                 # noqa: BLE001 -- reported below, then the NCCL fallback is used
+        err = repr(e)
+    outcomes = [None] * dist.get_world_size(group)
+    dist.all_gather_object(outcomes, err, group=group)     # also the barrier: every mailbox zeroed and mapped
+    if any(o is not None for o in outcomes):
+        if xchg is not None:
+            xchg.close()
+        xchg = None
+        if dist.get_rank(group) == 0:
+            import warnings
+            warnings.warn("uaps_b200: peer-memory exchange unavailable, using the NCCL all-reduce for the loss sums: "
+                          + "; ".join(o for o in outcomes if o is not None)[:300])
+    if xchg is not None:
+        _owned.append(xchg)
+    return xchg
 
 
 def exchange_for(group, device: torch.device) -> Optional[LossExchange]:
-    """The exchange of (group, device), created on first use; None when the group cannot use peer memory
-    (not NCCL, ranks on several hosts, more than 8 ranks, or UAPS_LOSS_EXCHANGE=nccl)."""
+    """The shared, host-epoch exchange of (group, device), created on first use (see ``new_exchange`` for None)."""
     if not dist.is_initialized():
         return None
     key = (id(group) if group is not None else 0, device.index)
     if key not in _exchanges:
-        ok = (os.environ.get("UAPS_LOSS_EXCHANGE", "peer") != "nccl" and dist.get_backend(group) == "nccl"
-              and 1 < dist.get_world_size(group) <= MAX_RANKS)
-        if ok:                                   # collective decision: every rank must take the same branch
-            hosts = [None] * dist.get_world_size(group)
-            dist.all_gather_object(hosts, socket.gethostname(), group=group)
-            ok = len(set(hosts)) == 1
-        xchg = None
-        if ok:
-            # mapping a peer's mailbox can fail (no P2P path, IPC disabled in the container ...): every rank must then
-            # take the NCCL route, so the outcome is agreed on collectively before anybody uses the exchange
-            err = None
-            try:
-                xchg = LossExchange(group, device)
-            except Exception as e:                 # noqa: BLE001 -- reported below, then the NCCL fallback is used
-                err = repr(e)
-            outcomes = [None] * dist.get_world_size(group)
-            dist.all_gather_object(outcomes, err, group=group)     # also the barrier: every mailbox zeroed and mapped
-            if any(o is not None for o in outcomes):
-                if xchg is not None:
-                    xchg.close()
-                xchg = None
-                if dist.get_rank(group) == 0:
-                    import warnings
-                    warnings.warn("uaps_b200: peer-memory exchange unavailable, using the NCCL all-reduce for the loss sums: "
-                                  + "; ".join(o for o in outcomes if o is not None)[:300])
-        _exchanges[key] = xchg
+        _exchanges[key] = new_exchange(group, device)
     return _exchanges[key]
 
 
 def close_all() -> None:
-    for x in _exchanges.values():
-        if x is not None:
-            x.close()
+    for x in _owned:
+        x.close()
+    _owned.clear()
     _exchanges.clear()

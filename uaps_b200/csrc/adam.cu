@@ -14,7 +14,19 @@ __global__ void __launch_bounds__(AT) adam_kernel(float4* __restrict__ p, const 
                                                   float4* __restrict__ v, long long n4, float* __restrict__ pt,
                                                   const float* __restrict__ gt, float* __restrict__ mt, float* __restrict__ vt,
                                                   int tail, float b1, float b2, float step_size, float inv_bc2_sqrt, float eps,
-                                                  float grad_scale) {
+                                                  float grad_scale, UapsStepState* __restrict__ state,
+                                                  const float* __restrict__ guard) {
+    if (state != nullptr) {                       // device-resident step: uaps_step_begin computed the bias corrections
+        step_size = state->adam_step_size;
+        inv_bc2_sqrt = state->adam_inv_bc2_sqrt;
+        if (guard != nullptr) {
+            const float gv = *guard;
+            if (!(fabsf(gv) <= 3.0e38f)) {        // NaN / inf loss (e.g. an exchange that timed out): leave p, m, v untouched
+                if (blockIdx.x == 0 && threadIdx.x == 0) { state->skipped = 1; state->n_skipped += 1; }
+                return;
+            }
+        }
+    }
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
         gg *= grad_scale;
         mm = fmaf(b1, mm, (1.f - b1) * gg);                          // exp_avg.lerp_(grad, 1 - beta1)
@@ -39,8 +51,11 @@ using namespace uaps;
 // p, g, m, v: device fp32 arrays of n elements, 16-byte aligned.  step: 1, 2, 3, ... (bias correction).
 // grad_scale multiplies the gradient first (1 for the SUM-all-reduced gradient of a globally normalised loss).
 UAPS_API int uaps_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t step, float lr, float beta1,
-                            float beta2, float eps, float grad_scale, cudaStream_t stream) {
-    if (p == nullptr || g == nullptr || m == nullptr || v == nullptr || n <= 0 || step < 1) return UAPS_EINVAL;
+                            float beta2, float eps, float grad_scale, UapsStepState* state, const float* guard,
+                            cudaStream_t stream) {
+    if (p == nullptr || g == nullptr || m == nullptr || v == nullptr || n <= 0) return UAPS_EINVAL;
+    if (state == nullptr && (step < 1 || guard != nullptr)) return UAPS_EINVAL;
+    if (state != nullptr) step = 1;               // unused: the kernel reads the device state
     if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f)) return UAPS_ERANGE;
     if (!aligned_to(p, 16) || !aligned_to(g, 16) || !aligned_to(m, 16) || !aligned_to(v, 16)) return UAPS_EALIGN;
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
@@ -51,7 +66,7 @@ UAPS_API int uaps_adam_step(float* p, const float* g, float* m, float* v, int64_
     const int grid = (int)(want < cap ? want : cap);
     adam_kernel<<<grid, AT, 0, stream>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
                                          reinterpret_cast<float4*>(v), n4, p + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, tail, beta1,
-                                         beta2, step_size, inv_bc2_sqrt, eps, grad_scale);
+                                         beta2, step_size, inv_bc2_sqrt, eps, grad_scale, state, guard);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }

@@ -136,7 +136,9 @@ struct BnParams {
     long long npix;
     int G;
     float* dgamma_accum; float* dbeta_accum;      // backward: optional fp32 gradient buffers to accumulate into
+    const uint64_t* seed_dev;                     // nullable: per-iteration key added to `seed` (UapsStepState.key_rank)
 };
+__device__ __forceinline__ uint64_t eff_seed(const BnParams& p) { return p.seed + (p.seed_dev != nullptr ? *p.seed_dev : 0ull); }
 
 // forward: a = dropout(leaky_relu(gamma * (y - mean) * rstd + beta))
 __global__ void __launch_bounds__(BT) bn_act_kernel(const uint4* __restrict__ y, uint4* __restrict__ out, const BnParams p) {
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(BT) bn_act_kernel(const uint4* __restrict__ y,
     }
     __syncthreads();
     const int chunk = threadIdx.x % p.G;
+    const uint64_t seed = p.p > 0.f ? eff_seed(p) : 0ull;
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = s_scale[chunk * 8 + i]; sh[i] = s_shift[chunk * 8 + i]; }
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(BT) bn_act_kernel(const uint4* __restrict__ y,
     stream_chunks<4>(total, [&](long long t) { return __ldg(y + t); }, [&](long long t, const uint4& r) {
         float v[8], k[8];
         unpack8(r, v);
-        if (p.p > 0.f) keep8(p.seed, (uint64_t)t, p.p, k);
+        if (p.p > 0.f) keep8(seed, (uint64_t)t, p.p, k);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float z = fmaf(v[i], sc[i], sh[i]);
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(BT) bn_act_bwd_reduce_kernel(const uint4* __re
                                                                double* __restrict__ sum_gx) {
     __shared__ float s_a[256], s_b[256];
     const int chunk = threadIdx.x % p.G;
+    const uint64_t seed = p.p > 0.f ? eff_seed(p) : 0ull;
     float mean[8], rstd[8], ga[8], be[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(BT) bn_act_bwd_reduce_kernel(const uint4* __re
         float gv[8], v[8], k[8];
         unpack8(pk.g, gv);
         unpack8(pk.y, v);
-        if (p.p > 0.f) keep8(p.seed, (uint64_t)t, p.p, k);
+        if (p.p > 0.f) keep8(seed, (uint64_t)t, p.p, k);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float xh = (v[i] - mean[i]) * rstd[i];
@@ -225,6 +229,7 @@ __global__ void __launch_bounds__(BT) bn_act_bwd_kernel(const uint4* __restrict_
         }
     }
     const int chunk = threadIdx.x % p.G;
+    const uint64_t seed = p.p > 0.f ? eff_seed(p) : 0ull;
     const float invn = (float)(1.0 / (double)p.npix);
     float mean[8], rstd[8], ga[8], be[8], mg[8], mgx[8];
 #pragma unroll
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(BT) bn_act_bwd_kernel(const uint4* __restrict_
         float gv[8], v[8], k[8];
         unpack8(pk.g, gv);
         unpack8(pk.y, v);
-        if (p.p > 0.f) keep8(p.seed, (uint64_t)t, p.p, k);
+        if (p.p > 0.f) keep8(seed, (uint64_t)t, p.p, k);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float xh = (v[i] - mean[i]) * rstd[i];
@@ -279,7 +284,7 @@ UAPS_API int uaps_bn_stats_nhwc(const void* y, int64_t npix, int C, double* sum,
 UAPS_API int uaps_bn_act_nhwc(const void* y, const double* sum, const double* sumsq, const float* gamma, const float* beta,
                               float* running_mean, float* running_var, float momentum, float eps, float slope, double p_drop,
                               uint64_t seed, void* out, float* save_mean, float* save_rstd, int64_t npix, int C,
-                              cudaStream_t stream) {
+                              const uint64_t* seed_dev, cudaStream_t stream) {
     if (y == nullptr || sum == nullptr || sumsq == nullptr || gamma == nullptr || beta == nullptr || out == nullptr ||
         save_mean == nullptr || save_rstd == nullptr || npix <= 0)
         return UAPS_EINVAL;
@@ -289,6 +294,7 @@ UAPS_API int uaps_bn_act_nhwc(const void* y, const double* sum, const double* su
     p.sum = sum; p.sumsq = sumsq; p.gamma = gamma; p.beta = beta; p.running_mean = running_mean; p.running_var = running_var;
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.momentum = momentum; p.eps = eps; p.slope = slope; p.p = (float)p_drop;
     p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
+    p.seed_dev = seed_dev;
     bn_act_kernel<<<bn_grid(npix * (C / 8), 4), BT, 0, stream>>>(reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(out), p);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
@@ -297,7 +303,7 @@ UAPS_API int uaps_bn_act_nhwc(const void* y, const double* sum, const double* su
 UAPS_API int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float* gamma, const float* beta, const float* save_mean,
                                   const float* save_rstd, float slope, double p_drop, uint64_t seed, double* sum_g,
                                   double* sum_gx, void* dy, float* dgamma_accum, float* dbeta_accum, int64_t npix, int C,
-                                  cudaStream_t stream) {
+                                  const uint64_t* seed_dev, cudaStream_t stream) {
     if (g_out == nullptr || y == nullptr || gamma == nullptr || beta == nullptr || save_mean == nullptr || save_rstd == nullptr ||
         sum_g == nullptr || sum_gx == nullptr || dy == nullptr || npix <= 0)
         return UAPS_EINVAL;
@@ -308,7 +314,7 @@ UAPS_API int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float*
     p.save_rstd = const_cast<float*>(save_rstd); p.slope = slope; p.p = (float)p_drop;
     p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
     if ((dgamma_accum == nullptr) != (dbeta_accum == nullptr)) return UAPS_EINVAL;
-    p.dgamma_accum = dgamma_accum; p.dbeta_accum = dbeta_accum;
+    p.dgamma_accum = dgamma_accum; p.dbeta_accum = dbeta_accum; p.seed_dev = seed_dev;
     const int grid = bn_grid(npix * (C / 8), 2);       // ~124 registers: 2 resident CTAs/SM = one persistent wave
     // sum_g / sum_gx (zeroed by the caller) receive sum(g') and sum(g' * xhat) = d beta and d gamma
     bn_act_bwd_reduce_kernel<<<bn_grid(npix * (C / 8), 2), BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y), p,

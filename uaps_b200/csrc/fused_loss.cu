@@ -19,10 +19,10 @@ namespace {
 using namespace loss;
 
 int check_common(const float* const* z, int K, int B, int C, int64_t HW, const float* mix_w,
-                 const int64_t* labels) {
+                 const int64_t* labels, const float* wcw_dev) {
     if (z == nullptr || B <= 0 || HW <= 0) return UAPS_EINVAL;
     if (K < 1 || K > KMAX || C < 2 || C > CMAX) return UAPS_ERANGE;
-    if (labels == nullptr && mix_w == nullptr) return UAPS_EINVAL;
+    if (labels == nullptr && mix_w == nullptr && wcw_dev == nullptr) return UAPS_EINVAL;
     if ((double)B * (double)HW >= 2147483648.0) return UAPS_ERANGE;
     for (int k = 0; k < K; ++k) {
         if (z[k] == nullptr) return UAPS_EINVAL;
@@ -91,6 +91,7 @@ struct ExchangeArgs {
     char* box[XCHG_WMAX];        // mailbox of every rank as mapped into THIS process (own one at [rank])
     int rank, world;
     unsigned epoch;              // 1, 2, 3, ... identical on all ranks for one exchange
+    const unsigned* epoch_dev;   // nullable: the epoch used is *epoch_dev + epoch (UapsStepState.xchg_base)
     unsigned long long timeout_ns;
 };
 
@@ -109,14 +110,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const float* __restrict__ partials, int S, unsigned nblocks,
                                                                             double* __restrict__ sums, const ExchangeArgs x, int K,
                                                                             int C, double N, float cw1, float cw2, int supervised,
-                                                                            float* __restrict__ sc, int nsc) {
+                                                                            float* __restrict__ sc, int nsc,
+                                                                            const float* __restrict__ wcw_dev) {
     __shared__ double s_sums[XCHG_SLOT];
     __shared__ double s_term[KMAX * CMAX];
+    __shared__ int s_timed_out;
     pdl_trigger();
     pdl_wait();
+    const unsigned epoch = x.epoch + (x.epoch_dev != nullptr ? *x.epoch_dev : 0u);
+    if (wcw_dev != nullptr) { cw1 = wcw_dev[UAPS_WCW_CW1]; cw2 = wcw_dev[UAPS_WCW_CW2]; }
+    if (threadIdx.x == 0) s_timed_out = 0;
     cta_fold_rows(partials, S, nblocks, s_sums);                 // local fold, as loss_fold_finalize_kernel
     __shared__ unsigned s_words[XCHG_WMAX][2 * XCHG_SLOT];
-    const int ph = x.epoch & 1;
+    const int ph = epoch & 1;
     const int nw = 2 * S;                                        // 32-bit halves of my S doubles
     // scatter: word idx of my sums -> slot [ph][rank][idx] of EVERY mailbox (peer stores travel over NVLink), tagged with the epoch
     for (int t = threadIdx.x; t < x.world * nw; t += blockDim.x) {
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const
         const unsigned bits = reinterpret_cast<const unsigned*>(s_sums)[idx];
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(x.box[p]) +
                                   ((size_t)(ph * XCHG_WMAX + x.rank) * 2 * XCHG_SLOT + idx);
-        st_word_sys(dst, bits, x.epoch);
+        st_word_sys(dst, bits, epoch);
     }
     // gather: every word of every source in MY mailbox, as soon as its tag shows this epoch (the other phase's words
     // carry epoch - 1, this phase's stale ones epoch - 2).  Bounded spin: a dead peer must not hang the GPU -- on timeout
@@ -138,15 +144,19 @@ __global__ void __launch_bounds__(1024) loss_fold_exchange_finalize_kernel(const
         const unsigned long long t0 = global_timer_ns();
         for (;;) {
             ld_word_sys(src, data, flag);
-            if (flag == x.epoch) break;
-            if (global_timer_ns() - t0 > x.timeout_ns) { timed_out = 1; break; }
+            if (flag == epoch) break;
+            // one thread timing out ends every thread's wait (the time-outs must not add up word after word)
+            if (*reinterpret_cast<volatile int*>(&s_timed_out) != 0 || global_timer_ns() - t0 > x.timeout_ns) {
+                s_timed_out = 1; timed_out = 1; break;
+            }
         }
+        if (timed_out) break;
         s_words[p][idx] = data;
     }
     timed_out = __syncthreads_or(timed_out);
     if (timed_out) {
         for (int i = threadIdx.x; i < nsc; i += blockDim.x) sc[i] = __int_as_float(0x7fc00000);
-        if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(x.box[x.rank] + XCHG_STATUS_OFF) = x.epoch;
+        if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(x.box[x.rank] + XCHG_STATUS_OFF) = epoch;
         return;
     }
     if (threadIdx.x < S) {
@@ -182,8 +192,9 @@ UAPS_API size_t uaps_loss_workspace_bytes(int K, int C) {
 static int loss_pass1_impl(const float* const* z, int K, int B, int C, int64_t HW,
                                const float* mix_w, const int64_t* labels, void* workspace, double* sums,
                                int64_t* pseudo_out, float* const* exp_var_out, int flags, cudaStream_t stream,
-                          int64_t N_global, float cw1, float cw2, float* scalars, const ExchangeArgs* xchg = nullptr) {
-    int rc = check_common(z, K, B, C, HW, mix_w, labels);
+                          int64_t N_global, float cw1, float cw2, float* scalars, const ExchangeArgs* xchg = nullptr,
+                          const float* wcw_dev = nullptr) {
+    int rc = check_common(z, K, B, C, HW, mix_w, labels, wcw_dev);
     if (rc != UAPS_OK) return rc;
     if (workspace == nullptr || sums == nullptr) return UAPS_EINVAL;
     if (!aligned_to(workspace, 16) || !aligned_to(sums, 8)) return UAPS_EALIGN;
@@ -198,7 +209,7 @@ static int loss_pass1_impl(const float* const* z, int K, int B, int C, int64_t H
             a.write_ev = 1;
         }
     }
-    a.labels = labels; a.pseudo = pseudo_out; a.HW = HW; a.B = B;
+    a.labels = labels; a.pseudo = pseudo_out; a.HW = HW; a.B = B; a.w_dev = labels == nullptr ? wcw_dev : nullptr;
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + WS_HEADER_BYTES);
     const int impl = pick_impl(pick_vec(z, exp_var_out, K, HW), flags, false);
     int nblocks = 0;
@@ -208,10 +219,10 @@ static int loss_pass1_impl(const float* const* z, int K, int B, int C, int64_t H
     if (xchg != nullptr)
         rc = (int)launch_pdl(loss_fold_exchange_finalize_kernel, dim3(1), dim3(1024), stream, pdl_enabled(), (const float*)partials, S,
                              (unsigned)nblocks, sums, *xchg, K, C, (double)N_global, cw1, cw2, (int)(labels != nullptr), scalars,
-                             scalars_count(K, C));
+                             scalars_count(K, C), wcw_dev);
     else if (scalars != nullptr)
         rc = (int)launch_pdl(loss_fold_finalize_kernel, dim3(1), dim3(1024), stream, pdl_enabled(), (const float*)partials, S,
-                             (unsigned)nblocks, sums, K, C, (double)N_global, cw1, cw2, (int)(labels != nullptr), scalars);
+                             (unsigned)nblocks, sums, K, C, (double)N_global, cw1, cw2, (int)(labels != nullptr), scalars, wcw_dev);
     else
         rc = (int)launch_pdl(loss_fold_kernel, dim3(ceil_div(S, 256 / kWarp)), dim3(256), stream, pdl_enabled(), (const float*)partials,
                              S, (unsigned)nblocks, sums);
@@ -231,10 +242,11 @@ UAPS_API int uaps_loss_pass1(const float* const* z, int K, int B, int C, int64_t
 UAPS_API int uaps_loss_pass1_scalars(const float* const* z, int K, int B, int C, int64_t HW, const float* mix_w,
                                      const int64_t* labels, void* workspace, double* sums, int64_t* pseudo_out,
                                      float* const* exp_var_out, int flags, float cw1, float cw2, float* scalars,
-                                     cudaStream_t stream) {
+                                     const float* wcw_dev, cudaStream_t stream) {
     if (scalars == nullptr || !aligned_to(scalars, 4)) return UAPS_EINVAL;
+    if (wcw_dev != nullptr && !aligned_to(wcw_dev, 4)) return UAPS_EALIGN;
     return loss_pass1_impl(z, K, B, C, HW, mix_w, labels, workspace, sums, pseudo_out, exp_var_out, flags, stream,
-                           (int64_t)B * HW, cw1, cw2, scalars);
+                           (int64_t)B * HW, cw1, cw2, scalars, nullptr, wcw_dev);
 }
 
 // ---- exchange mailboxes (multi-GPU, one process per GPU on one NVLink domain) ---------------------------------
@@ -278,8 +290,9 @@ UAPS_API int uaps_loss_pass1_exchange(const float* const* z, int K, int B, int C
                                       const int64_t* labels, void* workspace, double* sums, int64_t* pseudo_out,
                                       float* const* exp_var_out, int flags, void* const* mailboxes, int rank, int world,
                                       unsigned epoch, int64_t N_global, float cw1, float cw2, float* scalars,
-                                      cudaStream_t stream) {
+                                      const float* wcw_dev, const uint32_t* epoch_dev, cudaStream_t stream) {
     if (scalars == nullptr || mailboxes == nullptr || N_global <= 0 || epoch == 0) return UAPS_EINVAL;
+    if ((wcw_dev != nullptr && !aligned_to(wcw_dev, 4)) || (epoch_dev != nullptr && !aligned_to(epoch_dev, 4))) return UAPS_EALIGN;
     if (world < 1 || world > XCHG_WMAX || rank < 0 || rank >= world) return UAPS_ERANGE;
     if (!aligned_to(scalars, 4)) return UAPS_EALIGN;
     ExchangeArgs x{};
@@ -288,11 +301,13 @@ UAPS_API int uaps_loss_pass1_exchange(const float* const* z, int K, int B, int C
         if (!aligned_to(mailboxes[p], 128)) return UAPS_EALIGN;
         x.box[p] = reinterpret_cast<char*>(mailboxes[p]);
     }
-    x.rank = rank; x.world = world; x.epoch = epoch;
+    x.rank = rank; x.world = world; x.epoch = epoch; x.epoch_dev = epoch_dev;
+    // A peer may legitimately be seconds late (first-iteration lazy initialisation, a dataloader stall, rank 0 writing a
+    // checkpoint): the default wait is 30 s.  It stays bounded so that a dead peer can never hang the GPU.
     const char* tmo = getenv("UAPS_XCHG_TIMEOUT_MS");
-    x.timeout_ns = (tmo ? strtoull(tmo, nullptr, 10) : 4000ull) * 1000000ull;
+    x.timeout_ns = (tmo ? strtoull(tmo, nullptr, 10) : 30000ull) * 1000000ull;
     return loss_pass1_impl(z, K, B, C, HW, mix_w, labels, workspace, sums, pseudo_out, exp_var_out, flags, stream, N_global, cw1,
-                           cw2, scalars, &x);
+                           cw2, scalars, &x, wcw_dev);
 }
 
 
@@ -310,8 +325,8 @@ UAPS_API int uaps_loss_finalize(const double* sums_global, int K, int C, int64_t
 
 UAPS_API int uaps_loss_pass2(const float* const* z, int K, int B, int C, int64_t HW, const float* mix_w,
                                const int64_t* labels, const float* scalars, const float* grad_out,
-                               float* const* dz, int flags, cudaStream_t stream) {
-    int rc = check_common(z, K, B, C, HW, mix_w, labels);
+                               float* const* dz, int flags, const float* wcw_dev, cudaStream_t stream) {
+    int rc = check_common(z, K, B, C, HW, mix_w, labels, wcw_dev);
     if (rc != UAPS_OK) return rc;
     if (scalars == nullptr || grad_out == nullptr || dz == nullptr) return UAPS_EINVAL;
     LossArgs a{};
@@ -322,7 +337,7 @@ UAPS_API int uaps_loss_pass2(const float* const* z, int K, int B, int C, int64_t
         a.w[k] = mix_w ? mix_w[k] : 0.f;
         a.out[k] = dz[k];
     }
-    a.labels = labels; a.pseudo = nullptr; a.HW = HW; a.B = B;
+    a.labels = labels; a.pseudo = nullptr; a.HW = HW; a.B = B; a.w_dev = labels == nullptr ? wcw_dev : nullptr;
     const int impl = pick_impl(pick_vec(z, dz, K, HW), flags, true);
     int nblocks = 0;
     return dispatch_k(K, C, impl, labels != nullptr, true, a, nullptr, scalars, grad_out, &nblocks, stream);

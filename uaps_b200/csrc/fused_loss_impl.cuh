@@ -64,6 +64,7 @@ struct LossArgs {
     const float* z[KMAX];
     float* out[KMAX];            // pass1: exp_var_out (nullable entries); pass2: dz
     float w[KMAX];
+    const float* w_dev;          // nullable: device copy of the mix weights (UapsStepState.mix_w) that overrides w[]
     const int64_t* labels;       // supervised mode
     int64_t* pseudo;             // pass1 optional
     long long HW;
@@ -195,7 +196,7 @@ __device__ __noinline__ int argmax_exact_gmem(const LossArgs& a, size_t pix_off)
 #pragma unroll
         for (int c = 0; c < C; ++c) z[c] = __ldg(a.z[k] + pix_off + (size_t)c * a.HW);
         softmax_exact<C>(z, p[k], l);
-        w[k] = a.w[k];
+        w[k] = a.w_dev != nullptr ? a.w_dev[k] : a.w[k];
     }
     return argmax_exact<K, C>(p, w);
 }
@@ -365,7 +366,7 @@ loss_pass1_kernel(const __grid_constant__ LossArgs a, float* __restrict__ partia
 
     float w[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) w[k] = a.w[k];
+    for (int k = 0; k < K; ++k) w[k] = a.w_dev != nullptr ? a.w_dev[k] : a.w[k];
 
     float acc[S];
 #pragma unroll
@@ -536,13 +537,15 @@ __device__ void finalize_from_sums(const double* sums, int K, int C, double N, f
 
 __global__ void __launch_bounds__(1024) loss_fold_finalize_kernel(const float* __restrict__ partials, int S, unsigned nblocks,
                                                                    double* __restrict__ sums, int K, int C, double N, float cw1,
-                                                                   float cw2, int supervised, float* __restrict__ sc) {
+                                                                   float cw2, int supervised, float* __restrict__ sc,
+                                                                   const float* __restrict__ wcw_dev) {
     __shared__ double s_sums[3 * KMAX + 2 * KMAX * CMAX + CMAX];
     __shared__ double s_term[KMAX * CMAX];
     pdl_trigger();                    // pass 2 may start prefetching its logits now; it waits for THIS kernel before using sc
     pdl_wait();                       // partials of pass 1
     cta_fold_rows(partials, S, nblocks, s_sums);
     if (threadIdx.x < S) sums[threadIdx.x] = s_sums[threadIdx.x];
+    if (wcw_dev != nullptr) { cw1 = wcw_dev[UAPS_WCW_CW1]; cw2 = wcw_dev[UAPS_WCW_CW2]; }
     cta_finalize(s_sums, K, C, N, cw1, cw2, supervised, sc, s_term);
 }
 
@@ -684,7 +687,7 @@ loss_pass2_kernel(const __grid_constant__ LossArgs a, const float* __restrict__ 
 
     float w[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) w[k] = a.w[k];
+    for (int k = 0; k < K; ++k) w[k] = a.w_dev != nullptr ? a.w_dev[k] : a.w[k];
 
     // software pipelining (PF): the next group's K*C loads are issued before this group is computed, so
     // HBM latency overlaps the ~330 instructions/pixel instead of stalling the first consumer

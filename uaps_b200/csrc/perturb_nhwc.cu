@@ -74,7 +74,10 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
                                                            uint64_t seed, float range, float p, float scale,
                                                            const float* __restrict__ attention, const uint32_t* __restrict__ smax_enc,
                                                            float u, uint4* __restrict__ y_noise, uint4* __restrict__ y_drop,
-                                                           uint4* __restrict__ y_fdrop, uint4* __restrict__ dx, int G, long long HW, int B) {
+                                                           uint4* __restrict__ y_fdrop, uint4* __restrict__ dx, int G, long long HW, int B,
+                                                           const uint64_t* __restrict__ seed_dev, const float* __restrict__ u_dev) {
+    if (seed_dev != nullptr) seed += *seed_dev;       // device-resident step state (uaps_step_begin)
+    if (u_dev != nullptr) u = *u_dev;
     const long long chunks_per_sample = HW * G;
     const long long total = chunks_per_sample * B;
     for (long long t = (long long)blockIdx.x * PT + threadIdx.x; t < total; t += (long long)gridDim.x * PT) {
@@ -84,8 +87,11 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
         float nz[8], kp[8];
         uniform8(seed, (uint64_t)in_sample, kStreamNoise, nz);          // shared by the batch: keyed by the in-sample index
         uniform8(seed, (uint64_t)t, kStreamDrop, kp);
-        const float thr = __fmul_rn(dec_ordered(smax_enc[b]), u);
-        const float m = (attention[(size_t)b * HW + pix] < thr) ? 1.f : 0.f;
+        float m = 0.f;                                                   // FeatureDropout mask; its inputs exist only when that branch is live
+        if ((BWD ? (const void*)g_fdrop : (const void*)y_fdrop) != nullptr) {
+            const float thr = __fmul_rn(dec_ordered(smax_enc[b]), u);
+            m = (attention[(size_t)b * HW + pix] < thr) ? 1.f : 0.f;
+        }
         float o[8];
         if constexpr (!BWD) {
             float v[8];
@@ -157,8 +163,9 @@ UAPS_API int uaps_fdrop_stats_nhwc(const void* x, int B, int C, int64_t HW, floa
 
 UAPS_API int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range, double p_drop, const float* attention,
                                 const uint32_t* smax_enc, float u, void* y_noise, void* y_drop, void* y_fdrop, int B, int C,
-                                int64_t HW, cudaStream_t stream) {
-    if (x == nullptr || attention == nullptr || smax_enc == nullptr || B <= 0 || HW <= 0) return UAPS_EINVAL;
+                                int64_t HW, const uint64_t* seed_dev, const float* u_dev, cudaStream_t stream) {
+    if (x == nullptr || B <= 0 || HW <= 0) return UAPS_EINVAL;
+    if (y_fdrop != nullptr && (attention == nullptr || smax_enc == nullptr)) return UAPS_EINVAL;   // only FeatureDropout needs the statistics
     if (y_noise == nullptr && y_drop == nullptr && y_fdrop == nullptr) return UAPS_EINVAL;
     if (!valid_g(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
     if (!aligned_to(x, 16) || !aligned_to(y_noise, 16) || !aligned_to(y_drop, 16) || !aligned_to(y_fdrop, 16)) return UAPS_EALIGN;
@@ -166,15 +173,17 @@ UAPS_API int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range,
     perturb3_nhwc_kernel<false><<<grid1d(HW * (C / 8) * B), PT, 0, stream>>>(
         reinterpret_cast<const uint4*>(x), nullptr, nullptr, nullptr, seed, noise_range, (float)p_drop, (float)(1.0 / (double)pk),
         attention, smax_enc, u, reinterpret_cast<uint4*>(y_noise), reinterpret_cast<uint4*>(y_drop),
-        reinterpret_cast<uint4*>(y_fdrop), nullptr, C / 8, HW, B);
+        reinterpret_cast<uint4*>(y_fdrop), nullptr, C / 8, HW, B, seed_dev, u_dev);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
 
 UAPS_API int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, const void* g_fdrop, uint64_t seed,
                                     float noise_range, double p_drop, const float* attention, const uint32_t* smax_enc,
-                                    float u, void* dx, int B, int C, int64_t HW, cudaStream_t stream) {
-    if (dx == nullptr || attention == nullptr || smax_enc == nullptr || B <= 0 || HW <= 0) return UAPS_EINVAL;
+                                    float u, void* dx, int B, int C, int64_t HW, const uint64_t* seed_dev, const float* u_dev,
+                                    cudaStream_t stream) {
+    if (dx == nullptr || B <= 0 || HW <= 0) return UAPS_EINVAL;
+    if (g_fdrop != nullptr && (attention == nullptr || smax_enc == nullptr)) return UAPS_EINVAL;
     if (g_noise == nullptr && g_drop == nullptr && g_fdrop == nullptr) return UAPS_EINVAL;
     if (!valid_g(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
     if (!aligned_to(dx, 16) || !aligned_to(g_noise, 16) || !aligned_to(g_drop, 16) || !aligned_to(g_fdrop, 16)) return UAPS_EALIGN;
@@ -182,7 +191,7 @@ UAPS_API int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, con
     perturb3_nhwc_kernel<true><<<grid1d(HW * (C / 8) * B), PT, 0, stream>>>(
         nullptr, reinterpret_cast<const uint4*>(g_noise), reinterpret_cast<const uint4*>(g_drop),
         reinterpret_cast<const uint4*>(g_fdrop), seed, noise_range, (float)p_drop, (float)(1.0 / (double)pk), attention, smax_enc, u,
-        nullptr, nullptr, nullptr, reinterpret_cast<uint4*>(dx), C / 8, HW, B);
+        nullptr, nullptr, nullptr, reinterpret_cast<uint4*>(dx), C / 8, HW, B, seed_dev, u_dev);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }

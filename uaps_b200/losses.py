@@ -21,16 +21,20 @@ import torch
 from . import _lib as L
 
 _workspaces = {}
+_WORKSPACE_CACHE_MAX = 32
 
 
 def _workspace(device: torch.device, K: int, C: int) -> torch.Tensor:
-    """Pass-1 scratch, zero-filled once per (device, stream, K, C) as the ABI requires."""
+    """Pass-1 scratch, zero-filled once per (device, stream, K, C) as the ABI requires.  The cache is bounded: the
+    least recently used entry goes first (a long-lived process that keeps creating streams must not leak)."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream, K, C)
-    ws = _workspaces.get(key)
+    ws = _workspaces.pop(key, None)
     if ws is None:
         nbytes = L.lib().uaps_loss_workspace_bytes(K, C)
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+        while len(_workspaces) >= _WORKSPACE_CACHE_MAX:
+            _workspaces.pop(next(iter(_workspaces)))
+    _workspaces[key] = ws                     # (re-)inserted last = most recently used
     return ws
 
 
@@ -67,7 +71,7 @@ class _FusedLossFn(torch.autograd.Function):
     """Shared autograd node for the unlabeled (labels=None) and supervised (labels given) modes."""
 
     @staticmethod
-    def forward(ctx, mix_w, cw1, cw2, labels, group, want_pseudo, want_exp_var, flags, n_global, *logits):
+    def forward(ctx, mix_w, cw1, cw2, labels, group, want_pseudo, want_exp_var, flags, n_global, dstate, *logits):
         zs, B, C, H, W = _prep_logits(logits)
         K, HW = len(zs), H * W
         dev = zs[0].device
@@ -79,10 +83,14 @@ class _FusedLossFn(torch.autograd.Function):
                 raise RuntimeError("labels must be int64 [B, H, W]")
             labels = labels.contiguous()
             w_arr = None
+        elif dstate is not None:                    # device-resident iteration: mix_w / cw1 / cw2 live in UapsStepState
+            w_arr = None
         else:
             if mix_w is None or len(mix_w) != K:
                 raise RuntimeError("mix_w must hold one weight per decoder")
             w_arr = L.float_array(mix_w)            # fp32 rounding = torch's python-scalar * tensor rule
+        # dstate = (DeviceStepState, LossExchange | None, epoch offset inside the iteration)
+        wcw_dev = dstate[0].ptr("mix_w") if (dstate is not None and not sup) else None
         with L.on_device(dev):
             sums = torch.empty(lib.uaps_loss_sums_count(K, C), dtype=torch.float64, device=dev)
             scalars = torch.empty(lib.uaps_loss_scalars_count(K, C), dtype=torch.float32, device=dev)
@@ -96,17 +104,25 @@ class _FusedLossFn(torch.autograd.Function):
                       _workspace(dev, K, C).data_ptr(), sums.data_ptr(),
                       None if pseudo is None else pseudo.data_ptr(),
                       None if exp_var is None else L.ptr_array(exp_var), flags)
-            if single:                               # no exchange between the passes: fold + finalize fused
-                L.check(lib.uaps_loss_pass1_scalars(*common, float(cw1), float(cw2), scalars.data_ptr(), L.stream_ptr()),
-                        "uaps_loss_pass1_scalars")
+            if dstate is not None and dstate[1] is not None:  # this trainer's own mailboxes, epochs counted on the device
+                xchg = dstate[1]
+                n_tot = int(n_global) if n_global else B * HW * xchg.world
+                L.check(lib.uaps_loss_pass1_exchange(*common, xchg.ptrs, xchg.rank, xchg.world, int(dstate[2]), n_tot,
+                                                     float(cw1), float(cw2), scalars.data_ptr(), wcw_dev,
+                                                     dstate[0].ptr("xchg_base"), L.stream_ptr()), "uaps_loss_pass1_exchange")
+            elif single:                             # no exchange between the passes: fold + finalize fused
+                L.check(lib.uaps_loss_pass1_scalars(*common, float(cw1), float(cw2), scalars.data_ptr(), wcw_dev,
+                                                    L.stream_ptr()), "uaps_loss_pass1_scalars")
             else:
+                if dstate is not None:
+                    raise RuntimeError("a device-resident iteration over several ranks needs the peer-memory exchange")
                 from .comm import exchange_for
                 xchg = exchange_for(group, dev) if dist.is_initialized() else None
                 if xchg is not None:                 # fold + NVLink peer-memory exchange + finalize in one kernel
                     n_tot = int(n_global) if n_global else B * HW * xchg.world
                     L.check(lib.uaps_loss_pass1_exchange(*common, xchg.ptrs, xchg.rank, xchg.world, xchg.next_epoch(), n_tot,
-                                                         float(cw1), float(cw2), scalars.data_ptr(), L.stream_ptr()),
-                            "uaps_loss_pass1_exchange")
+                                                         float(cw1), float(cw2), scalars.data_ptr(), None, None,
+                                                         L.stream_ptr()), "uaps_loss_pass1_exchange")
                 else:
                     L.check(lib.uaps_loss_pass1(*common, L.stream_ptr()), "uaps_loss_pass1")
                     world = _allreduce_sums(sums, group)
@@ -114,7 +130,7 @@ class _FusedLossFn(torch.autograd.Function):
                     L.check(lib.uaps_loss_finalize(sums.data_ptr(), K, C, n_tot, float(cw1), float(cw2), int(sup),
                                                    scalars.data_ptr(), L.stream_ptr()), "uaps_loss_finalize")
         ctx.save_for_backward(scalars, *([labels] if sup else []), *zs)
-        ctx.meta = (K, B, C, HW, sup, flags, tuple(float(w) for w in mix_w) if not sup else None)
+        ctx.meta = (K, B, C, HW, sup, flags, tuple(float(w) for w in mix_w) if (not sup and dstate is None) else None, wcw_dev)
         extra = []
         if pseudo is not None:
             extra.append(pseudo)
@@ -126,7 +142,7 @@ class _FusedLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_scalars, *_unused):
-        K, B, C, HW, sup, flags, mix_w = ctx.meta
+        K, B, C, HW, sup, flags, mix_w, wcw_dev = ctx.meta
         saved = ctx.saved_tensors
         scalars = saved[0]
         labels = saved[1] if sup else None
@@ -137,11 +153,11 @@ class _FusedLossFn(torch.autograd.Function):
         with L.on_device(dev):
             dz = [torch.empty_like(z) for z in zs]
             L.check(L.lib().uaps_loss_pass2(L.ptr_array(zs), K, B, C, HW,
-                                            None if sup else L.float_array(mix_w),
+                                            None if (sup or mix_w is None) else L.float_array(mix_w),
                                             labels.data_ptr() if sup else None,
                                             scalars.data_ptr(), grad_out.data_ptr(), L.ptr_array(dz),
-                                            flags, L.stream_ptr()), "uaps_loss_pass2")
-        return (None,) * 9 + tuple(dz)
+                                            flags, wcw_dev, L.stream_ptr()), "uaps_loss_pass2")
+        return (None,) * 10 + tuple(dz)
 
 
 def _split_extra(out, want_pseudo, want_exp_var):
@@ -150,9 +166,19 @@ def _split_extra(out, want_pseudo, want_exp_var):
     return pseudo, (rest if want_exp_var else None)
 
 
-def uaps_unlabeled_loss(logits: Sequence[torch.Tensor], mix_w: Sequence[float], cw1: float, cw2: float, *,
+def _dev_ctx(step_state):
+    """(DeviceStepState, LossExchange | None, epoch offset) for a loss call inside a device-resident iteration."""
+    if step_state is None:
+        return None
+    from . import stepctx
+    sc = stepctx.current()
+    xchg = sc.xchg if sc is not None else None
+    return (step_state, xchg, sc.next_xchg_offset() if xchg is not None else 0)
+
+
+def uaps_unlabeled_loss(logits: Sequence[torch.Tensor], mix_w: Optional[Sequence[float]], cw1: float, cw2: float, *,
                         group=None, return_pseudo: bool = False, return_exp_var: bool = False,
-                        exact_math: bool = False, n_global: Optional[int] = None):
+                        exact_math: bool = False, n_global: Optional[int] = None, step_state=None):
     """Unlabeled-batch loss of UAPS for K decoders (UAPS_train.py:186-189, 223-282).
 
     logits: K tensors [B, C, H, W] fp32 (main, aux1, ...); mix_w: the Dirichlet draw of :251 (K floats);
@@ -164,10 +190,14 @@ def uaps_unlabeled_loss(logits: Sequence[torch.Tensor], mix_w: Sequence[float], 
     Returns ``(loss_u, ps_loss, l_uncert, pseudo_label | None, exp_var | None)`` with
     loss_u = cw1 * ps_loss + cw2 * l_uncert (the unlabeled terms of :282), pseudo_label int64 [B,H,W]
     (bit-exact torch.argmax of the mix), exp_var a list of K [B,H,W] maps exp(-KL_k).
+
+    step_state: a ``stepctx.DeviceStepState`` -- mix_w, cw1 and cw2 are then read from device memory (whatever is
+    passed for them is ignored), which is what lets ``UAPSTrainer`` capture the iteration into a CUDA graph.
     """
     flags = L.LOSS_EXACT if exact_math else 0
-    out = _FusedLossFn.apply(tuple(float(w) for w in mix_w), cw1, cw2, None, group, return_pseudo,
-                             return_exp_var, flags, n_global, *logits)
+    out = _FusedLossFn.apply(None if step_state is not None else tuple(float(w) for w in mix_w),
+                             0.0 if step_state is not None else cw1, 0.0 if step_state is not None else cw2, None, group,
+                             return_pseudo, return_exp_var, flags, n_global, _dev_ctx(step_state), *logits)
     sc = out[0]
     pseudo, exp_var = _split_extra(out, return_pseudo, return_exp_var)
     return sc[L.SC_LOSS_U], sc[L.SC_PS_LOSS], sc[L.SC_L_UNCERT], pseudo, exp_var
@@ -178,7 +208,7 @@ def uaps_unlabeled_loss_terms(logits, mix_w, cw1, cw2, **kw):
     dict(ps_k, ebar_k, ce_k, dice_k) as detached [K] tensors."""
     flags = L.LOSS_EXACT if kw.pop("exact_math", False) else 0
     out = _FusedLossFn.apply(tuple(float(w) for w in mix_w), cw1, cw2, None, kw.get("group"), False, False,
-                             flags, kw.get("n_global"), *logits)
+                             flags, kw.get("n_global"), None, *logits)
     K = len(logits)
     sc, b = out[0], L.SC_BASE
     d = sc.detach()
@@ -188,11 +218,11 @@ def uaps_unlabeled_loss_terms(logits, mix_w, cw1, cw2, **kw):
 
 
 def uaps_supervised_loss(logits: Sequence[torch.Tensor], labels: torch.Tensor, *, group=None,
-                         exact_math: bool = False, n_global: Optional[int] = None):
+                         exact_math: bool = False, n_global: Optional[int] = None, step_state=None):
     """Labeled-batch loss (UAPS_train.py:194-218): returns (supervised_loss, total_loss_ce, total_loss_dice,
     ce_k[K]) where supervised_loss = mean_k 0.5 (CE_k + Dice_k); all three are differentiable."""
     flags = L.LOSS_EXACT if exact_math else 0
-    out = _FusedLossFn.apply(None, 1.0, 0.0, labels, group, False, False, flags, n_global, *logits)
+    out = _FusedLossFn.apply(None, 1.0, 0.0, labels, group, False, False, flags, n_global, _dev_ctx(step_state), *logits)
     K = len(logits)
     sc, b = out[0], L.SC_BASE
     return sc[L.SC_LOSS_U], sc[L.SC_MEAN_CE], sc[L.SC_MEAN_DICE], sc.detach()[b + 2 * K:b + 3 * K]
@@ -202,11 +232,11 @@ def dice_loss(true: torch.Tensor, logits: torch.Tensor, eps: float = 1e-7) -> to
     """Drop-in for utilities/pytorch_losses.py:54 ``dice_loss(true[B,1,H,W], logits[B,C,H,W])``."""
     if eps != 1e-7:
         raise RuntimeError("the fused kernel implements the reference's eps = 1e-7 only")
-    out = _FusedLossFn.apply(None, 1.0, 0.0, true.squeeze(1).long(), None, False, False, 0, None, logits)
+    out = _FusedLossFn.apply(None, 1.0, 0.0, true.squeeze(1).long(), None, False, False, 0, None, None, logits)
     return out[0][L.SC_MEAN_DICE]
 
 
 def ce_loss(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """Drop-in for the reference's ``CrossEntropyLoss()(logits, target[B,H,W])`` (UAPS_train.py:75)."""
-    out = _FusedLossFn.apply(None, 1.0, 0.0, target.long(), None, False, False, 0, None, logits)
+    out = _FusedLossFn.apply(None, 1.0, 0.0, target.long(), None, False, False, 0, None, None, logits)
     return out[0][L.SC_MEAN_CE]

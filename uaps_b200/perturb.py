@@ -21,14 +21,33 @@ from . import _lib as L
 
 # host-side source of Philox seeds and of FeatureDropout's u (reference: np.random global, :165)
 generator = np.random.default_rng(1337)
+_rank_mixed = False
 
 
-def manual_seed(seed: int) -> None:
-    global generator
-    generator = np.random.default_rng(seed)
+def manual_seed(seed: int, rank: int = 0) -> None:
+    """Re-seed the host generator.  ``rank``: each data-parallel rank must draw its own dropout masks and feature noise
+    (the reference's DataParallel replicas do, UAPS_model.py:13), so multi-rank callers pass their rank."""
+    global generator, _rank_mixed
+    generator = np.random.default_rng([int(seed), int(rank)] if rank else int(seed))
+    _rank_mixed = True
+
+
+def _mix_rank_once() -> None:
+    """First draw in a torch.distributed process with rank > 0 and no explicit manual_seed: fold the rank into the stream."""
+    global _rank_mixed
+    if _rank_mixed:
+        return
+    _rank_mixed = True
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_rank() > 0:
+            manual_seed(1337, dist.get_rank())
+    except Exception:               # noqa: BLE001 -- a seed stream, never a reason to fail
+        pass
 
 
 def _next_seed() -> int:
+    _mix_rank_once()
     return int(generator.integers(0, 2 ** 63 - 1))
 
 
@@ -209,45 +228,65 @@ def perturb3(x: torch.Tensor, *, noise: Optional[torch.Tensor] = None, keep: Opt
 # ---- channels-last bf16 variant (bf16 / tcgen05 model path) ------------------------------------------
 class _Perturb3NhwcFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, seed, rng, p, u):
+    def forward(ctx, x, seed, rng, p, u, seed_dev, u_dev, n_out):
         L.require_cuda(x)
         if x.dtype != torch.bfloat16 or not x.is_contiguous(memory_format=torch.channels_last):
             raise RuntimeError("perturb3_nhwc expects a channels_last bf16 [B,C,H,W] tensor")
         B, C, H, W = x.shape
-        attention = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
-        smax = torch.zeros(B, dtype=torch.int32, device=x.device)
-        ys = [torch.empty_like(x) for _ in range(3)]               # empty_like keeps channels_last
+        if n_out[2]:                                         # only FeatureDropout needs the channel-mean statistics
+            attention = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
+            smax = torch.zeros(B, dtype=torch.int32, device=x.device)
+        else:
+            attention = smax = torch.empty(0, dtype=torch.float32, device=x.device)
+        ys = [torch.empty_like(x) if n_out[i] else None for i in range(3)]      # empty_like keeps channels_last
         lib = L.lib()
+        ap, sp = (attention.data_ptr(), smax.data_ptr()) if n_out[2] else (None, None)
         with L.on_device(x.device):
-            L.check(lib.uaps_fdrop_stats_nhwc(x.data_ptr(), B, C, H * W, attention.data_ptr(), smax.data_ptr(),
-                                              L.stream_ptr()), "uaps_fdrop_stats_nhwc")
-            L.check(lib.uaps_perturb3_nhwc(x.data_ptr(), seed, rng, p, attention.data_ptr(), smax.data_ptr(), u,
-                                           ys[0].data_ptr(), ys[1].data_ptr(), ys[2].data_ptr(), B, C, H * W,
-                                           L.stream_ptr()), "uaps_perturb3_nhwc")
+            if n_out[2]:
+                L.check(lib.uaps_fdrop_stats_nhwc(x.data_ptr(), B, C, H * W, ap, sp, L.stream_ptr()), "uaps_fdrop_stats_nhwc")
+            L.check(lib.uaps_perturb3_nhwc(x.data_ptr(), seed, rng, p, ap, sp, u,
+                                           *[None if y is None else y.data_ptr() for y in ys], B, C, H * W,
+                                           seed_dev, u_dev, L.stream_ptr()), "uaps_perturb3_nhwc")
         ctx.save_for_backward(attention, smax)
-        ctx.args = (seed, rng, p, u)
+        ctx.args = (seed, rng, p, u, seed_dev, u_dev, n_out[2])
         return tuple(ys)
 
     @staticmethod
     def backward(ctx, g_noise, g_drop, g_fdrop):
         attention, smax = ctx.saved_tensors
-        seed, rng, p, u = ctx.args
+        seed, rng, p, u, seed_dev, u_dev, has_stats = ctx.args
         gs = [None if g is None else g.contiguous(memory_format=torch.channels_last) for g in (g_noise, g_drop, g_fdrop)]
         ref = next(g for g in gs if g is not None)
         B, C, H, W = ref.shape
         dx = torch.empty_like(ref)
         with L.on_device(ref.device):
             L.check(L.lib().uaps_perturb3_nhwc_bwd(*[None if g is None else g.data_ptr() for g in gs], seed, rng, p,
-                                                   attention.data_ptr(), smax.data_ptr(), u, dx.data_ptr(), B, C, H * W,
-                                                   L.stream_ptr()), "uaps_perturb3_nhwc_bwd")
-        return dx, None, None, None, None
+                                                   attention.data_ptr() if has_stats else None,
+                                                   smax.data_ptr() if has_stats else None, u, dx.data_ptr(), B, C, H * W,
+                                                   seed_dev, u_dev, L.stream_ptr()), "uaps_perturb3_nhwc_bwd")
+        return (dx,) + (None,) * 7
 
 
 def perturb3_nhwc(x: torch.Tensor, *, u: Optional[float] = None, seed: Optional[int] = None,
-                  uniform_range: float = 0.3, p: float = 0.5):
-    """Channels-last bf16 ``perturb3``: (FeatureNoise, Dropout, FeatureDropout) of one feature map in one pass."""
+                  uniform_range: float = 0.3, p: float = 0.5, outputs=(True, True, True)):
+    """Channels-last bf16 ``perturb3``: (FeatureNoise, Dropout, FeatureDropout) of one feature map in one pass.
+    ``outputs``: which of the three copies to produce (None for the others) -- a 4th / 5th auxiliary decoder (the K = 5
+    ablation) calls it again for ONE more copy of the perturbation family it re-uses, with a fresh draw.
+    Inside a device-resident iteration (``stepctx.current().state``) the Philox key and the threshold u come from the
+    device step state; otherwise they are drawn from ``uaps_b200.perturb.generator`` on the host."""
+    from . import stepctx
+    sc = stepctx.current()
+    seed_dev = u_dev = None
+    if sc is not None and sc.state is not None and seed is None and u is None:
+        seed, seed_dev = sc.next_seed(), sc.state.ptr("key_rank")
+        if outputs[2]:
+            u, u_dev = 0.8, sc.state.ptr("u", sc.next_u_slot())
+        else:
+            u = 0.8                                          # unused: no FeatureDropout copy requested
     if seed is None:
         seed = _next_seed()
     if u is None:
+        _mix_rank_once()
         u = float(generator.uniform(0.7, 0.9))
-    return _Perturb3NhwcFn.apply(x, int(seed), float(uniform_range), float(p), float(np.float32(u)))
+    return _Perturb3NhwcFn.apply(x, int(seed), float(uniform_range), float(p), float(np.float32(u)), seed_dev, u_dev,
+                                 tuple(bool(o) for o in outputs))

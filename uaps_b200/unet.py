@@ -65,16 +65,20 @@ def _decoder(class_num: int) -> nn.Module:
 
 
 class UNet_UAPS(nn.Module):
-    def __init__(self, in_chns: int, class_num: int, n_aux: int = 3, compute: str = "fp32"):
+    def __init__(self, in_chns: int, class_num: int, n_aux: int = 3, compute: str = "bf16"):
         super().__init__()
         if not 0 <= n_aux <= 5:
             raise ValueError("n_aux must be in [0, 5]")
+        if compute == "reference":
+            compute = "fp32"
         if compute not in ("fp32", "bf16"):
-            raise ValueError("compute must be 'fp32' or 'bf16'")
+            raise ValueError("compute must be 'bf16' (default), or 'fp32' / 'reference'")
         self.in_chns, self.class_num, self.n_aux = in_chns, class_num, n_aux
-        # "fp32": every layer in fp32 NCHW (cuDNN convs) -- the reference-precision path, 1e-5 parity.
-        # "bf16": channels-last bf16 activations, convolutions (forward + data gradient) on the
-        #         hand-written tcgen05 implicit-GEMM kernel, fp32 master weights, 1e-2 parity.
+        # "bf16" (default, the product path): channels-last bf16 activations, every layer a hand-written sm_100a
+        #         kernel (tcgen05 implicit-GEMM fprop / dgrad / wgrad, fused BN, resampling, Philox perturbations),
+        #         fp32 master weights and accumulation, 1e-2 parity.
+        # "fp32" / "reference": every layer in fp32 NCHW through torch (cuDNN) -- kept ONLY as the
+        #         reference-precision path for parity runs against the reference's golden vectors (1e-4).
         self.compute = compute
         self.encoder = _encoder(in_chns)
         self.main_decoder = _decoder(class_num)
@@ -117,15 +121,18 @@ class UNet_UAPS(nn.Module):
     def _block16(self, x, blk, p_drop, keep, x2=None):
         cc = blk.conv_conv
         c0, b0, c4, b4 = (cc.get_submodule(n) for n in ("0", "1", "4", "5"))
-        y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=False)
+        # a conv bias in front of a BatchNorm that uses BATCH statistics has an analytically zero gradient; with running
+        # statistics (eval mode, e.g. fine-tuning with frozen BN) it does not
+        bg = not self.training
+        y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=bg)
         if self.training and keep is None:
             # fused BN(batch stats) + LeakyReLU + Philox dropout: 2 kernels forward, 2 backward
             y = bn_lrelu_dropout(y, b0, p_drop)
-            return bn_lrelu_dropout(conv_bf16(y, c4.weight, c4.bias, bias_grad=False), b4, 0.0)
+            return bn_lrelu_dropout(conv_bf16(y, c4.weight, c4.bias, bias_grad=bg), b4, 0.0)
         y = F.leaky_relu(b0(y), 0.01)                         # eval mode / injected dropout mask (parity runs)
         if p_drop > 0.0 and self.training:
             y = y * (keep.to(y.dtype) * (1.0 / (1.0 - p_drop)))
-        return F.leaky_relu(b4(conv_bf16(y, c4.weight, c4.bias, bias_grad=False)), 0.01)
+        return F.leaky_relu(b4(conv_bf16(y, c4.weight, c4.bias, bias_grad=bg)), 0.01)
 
     def _encode16(self, x, enc_keep):
         B, C, H, W = x.shape
@@ -154,22 +161,30 @@ class UNet_UAPS(nn.Module):
         outs = [self._decode16(feats, self.main_decoder)]
         fused = None
         if rand is None and self.n_aux > 0:                    # one fused Philox kernel per level (rows a2-a4)
-            fused = [P.perturb3_nhwc(f) for f in feats]
+            live = tuple(a <= self.n_aux for a in (1, 2, 3))
+            fused = [P.perturb3_nhwc(f, outputs=live) for f in feats]
         for a in range(1, self.n_aux + 1):
             kind = _AUX_KINDS[(a - 1) % 3]
             if fused is not None and a <= 3:
                 outs.append(self._decode16([t[a - 1] for t in fused], self.get_submodule(f"aux_decoder{a}")))
                 continue
+            if rand is None:
+                # 4th / 5th auxiliary decoder (the K = 5 ablation; the reference has only commented ``aux4`` stubs,
+                # UAPS_train.py:139,182,190, so the perturbation is this repo's choice: the same three families in
+                # order, with a fresh draw): the same kernel, asked for the one copy it needs
+                sel = tuple(k == kind for k in _AUX_KINDS)
+                pf = [P.perturb3_nhwc(f, outputs=sel)[_AUX_KINDS.index(kind)] for f in feats]
+                outs.append(self._decode16(pf, self.get_submodule(f"aux_decoder{a}")))
+                continue
             pf = []
-            for lvl, f in enumerate(feats):                    # injected draws (parity runs) / 4th+ decoder: torch expressions
+            for lvl, f in enumerate(feats):                    # injected draws (parity runs only): torch expressions
                 if kind == "noise":
-                    n = rand["noise"][lvl].to(f.dtype) if rand is not None else \
-                        (torch.rand(f.shape[1:], device=f.device, dtype=torch.float32) * 0.6 - 0.3).to(f.dtype)
+                    n = rand["noise"][lvl].to(f.dtype)
                     pf.append(f * n.unsqueeze(0) + f)
                 elif kind == "dropout":
-                    pf.append(f * (rand["aux2_keep"][lvl].to(f.dtype) * 2.0) if rand is not None else F.dropout(f, 0.5, True))
+                    pf.append(f * (rand["aux2_keep"][lvl].to(f.dtype) * 2.0))
                 else:
-                    u = rand["u"][lvl] if rand is not None else float(P.generator.uniform(0.7, 0.9))
+                    u = rand["u"][lvl]
                     att = f.float().mean(dim=1, keepdim=True)
                     thr = att.flatten(1).max(dim=1)[0].view(-1, 1, 1, 1) * u
                     pf.append(f * (att < thr).to(f.dtype))
@@ -332,10 +347,12 @@ def load_checkpoint(path: str, model: nn.Module, optimizer=None, map_location=No
     return ck.get("epoch"), ck.get("best_dice_1")
 
 
-def net_factory(net_type: str = "unet_uaps", in_chns: int = 3, class_num: int = 4):
-    """utilities/UAPS_net_factory.py:5-13: the model on CUDA, or None for an unknown type."""
+def net_factory(net_type: str = "unet_uaps", in_chns: int = 3, class_num: int = 4, compute: str = "bf16"):
+    """utilities/UAPS_net_factory.py:5-13: the model on CUDA, or None for an unknown type.
+    The model it returns runs the hand-written sm_100a kernels (``compute="bf16"``); pass ``compute="reference"`` for the
+    fp32 torch/cuDNN path that exists for parity runs."""
     if net_type == "unet_uaps":
-        return UNet_UAPS(in_chns=in_chns, class_num=class_num).cuda()
+        return UNet_UAPS(in_chns=in_chns, class_num=class_num, compute=compute).cuda()
     if net_type == "unet":
-        return UNet_UAPS(in_chns=in_chns, class_num=class_num, n_aux=0).cuda()
+        return UNet_UAPS(in_chns=in_chns, class_num=class_num, n_aux=0, compute=compute).cuda()
     return None
