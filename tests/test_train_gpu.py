@@ -149,7 +149,7 @@ def test_step_begin_draws_ramp_and_adam_corrections_on_device():
         t = it - 7990 + 1
         assert sa.adam_step == t
         assert sa.adam_step_size == pytest.approx(1e-3 / (1 - 0.9 ** t), rel=1e-6)
-        assert sa.adam_inv_bc2_sqrt == pytest.approx(1 / math.sqrt(1 - 0.999 ** t), rel=1e-6)
+        assert sa.adam_inv_bc2_sqrt == pytest.approx(1 / math.sqrt(1 - 0.999 ** t), rel=2e-5)      # beta2 crosses the ABI as fp32
         assert (sa.xchg_base, sa.xchg_next) == (2 * (t - 1), 2 * t)
         seen.append((tuple(w), sa.key_rank))
     assert len(set(seen)) == 4                                            # fresh draws every iteration

@@ -356,7 +356,10 @@ __device__ __forceinline__ void block_store_partials(float (&acc)[S], float* __r
     }
 }
 
-template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF>
+// WDEV: the mix weights come from device memory (a.w_dev, the device-resident step state) instead of the by-value
+// argument block.  A template parameter, not a run-time select: by-value weights are constant-bank FMA operands and
+// cost no registers, and these kernels sit exactly at their register budget (a run-time select spilled).
+template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF, bool WDEV>
 __global__ void __launch_bounds__(LOSS_THREADS, min_ctas(K, C, PF ? 2 * VEC : VEC, true))
 loss_pass1_kernel(const __grid_constant__ LossArgs a, float* __restrict__ partials) {
     constexpr int S = sums_count(K, C);
@@ -366,7 +369,7 @@ loss_pass1_kernel(const __grid_constant__ LossArgs a, float* __restrict__ partia
 
     float w[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) w[k] = a.w_dev != nullptr ? a.w_dev[k] : a.w[k];
+    for (int k = 0; k < K; ++k) w[k] = WDEV ? a.w_dev[k] : a.w[k];
 
     float acc[S];
 #pragma unroll
@@ -680,14 +683,14 @@ __device__ __forceinline__ void pixel_backward(const PixelState<K, C>& st, const
     }
 }
 
-template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF>
+template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF, bool WDEV>
 __global__ void __launch_bounds__(LOSS_THREADS, min_ctas(K, C, PF ? 2 * VEC : VEC, false))
 loss_pass2_kernel(const __grid_constant__ LossArgs a, const float* __restrict__ sc, const float* __restrict__ grad_out) {
     __shared__ GradConsts<K, C> gc;
 
     float w[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) w[k] = a.w_dev != nullptr ? a.w_dev[k] : a.w[k];
+    for (int k = 0; k < K; ++k) w[k] = WDEV ? a.w_dev[k] : a.w[k];
 
     // software pipelining (PF): the next group's K*C loads are issued before this group is computed, so
     // HBM latency overlaps the ~330 instructions/pixel instead of stalling the first consumer
@@ -763,20 +766,20 @@ inline int grid_for(Kern kern, unsigned ngroups) {
     return (int)(want < cap ? want : cap);
 }
 
-template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF>
+template <int K, int C, int VEC, bool SUP, bool EXACT, bool PF, bool WDEV>
 inline int launch_reg(bool pass2, LossArgs a, float* partials, const float* sc, const float* go, int* nblocks,
                       cudaStream_t st) {
     a.groups_per_image = (unsigned)(a.HW / VEC);
     a.ngroups = (unsigned)a.B * a.groups_per_image;
     if (!pass2) {
-        auto kern = loss_pass1_kernel<K, C, VEC, SUP, EXACT, PF>;
+        auto kern = loss_pass1_kernel<K, C, VEC, SUP, EXACT, PF, WDEV>;
         static const int grid_cap = grid_for(kern, 0x7fffffffu);       // occupancy query once per instantiation
         const long long want = ceil_div<long long>(a.ngroups, LOSS_THREADS);
         *nblocks = (int)(want < grid_cap ? want : grid_cap);
         const cudaError_t e = launch_pdl(kern, dim3(*nblocks), dim3(LOSS_THREADS), st, pdl_enabled(), a, partials);
         if (e != cudaSuccess) return (int)e;
     } else {
-        auto kern = loss_pass2_kernel<K, C, VEC, SUP, EXACT, PF>;
+        auto kern = loss_pass2_kernel<K, C, VEC, SUP, EXACT, PF, WDEV>;
         static const int grid_cap = grid_for(kern, 0x7fffffffu);
         const long long want = ceil_div<long long>(a.ngroups, LOSS_THREADS);
         *nblocks = (int)(want < grid_cap ? want : grid_cap);
@@ -791,8 +794,9 @@ template <int K, int C>
 inline int launch_kc(int impl, bool sup, bool pass2, const LossArgs& a, float* partials, const float* sc,
                      const float* go, int* nblocks, cudaStream_t st) {
 #define UAPS_RUN(VEC, EXACT, PF)                                                                       \
-    (sup ? launch_reg<K, C, VEC, true, EXACT, PF>(pass2, a, partials, sc, go, nblocks, st)             \
-         : launch_reg<K, C, VEC, false, EXACT, PF>(pass2, a, partials, sc, go, nblocks, st))
+    (sup ? launch_reg<K, C, VEC, true, EXACT, PF, false>(pass2, a, partials, sc, go, nblocks, st)                      \
+         : (a.w_dev != nullptr ? launch_reg<K, C, VEC, false, EXACT, PF, true>(pass2, a, partials, sc, go, nblocks, st) \
+                               : launch_reg<K, C, VEC, false, EXACT, PF, false>(pass2, a, partials, sc, go, nblocks, st)))
     if (impl == IMPL_EXACT) return UAPS_RUN(1, true, false);
     if constexpr (has_vec4(K, C)) { if (impl == IMPL_VEC4_PF) return UAPS_RUN(4, false, true); }
     if constexpr (has_vec2(K, C)) { if (impl == IMPL_VEC4_PF || impl == IMPL_VEC2_PF) return UAPS_RUN(2, false, true); }
