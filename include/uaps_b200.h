@@ -338,6 +338,23 @@ int uaps_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int6
                                               skipped and state->skipped / n_skipped record it (needs state) */
                    cudaStream_t stream);
 
+/* ---- gradient all-reduce fused with the Adam step, over NVLink peer memory ------------------------------------------
+ * (replaces the gradient sum of nn.DataParallel, UAPS_model.py:13, plus optimizer_1.step(), UAPS_train.py:292, at N > 1.)
+ * Every rank's flat gradient buffer lives in a peer-mappable allocation (uaps_peer_alloc; exported / mapped / unmapped
+ * with uaps_xchg_export / _import / _close).  ONE kernel per rank: wait until every rank's gradients are complete, read
+ * all ranks' gradients (peers' over NVLink) and add them in rank order -- bit-identical sums on every rank --, apply the
+ * Adam update to the local replica, wait until every rank has finished reading.  No NCCL call, so the iteration stays a
+ * capturable kernel sequence.  grads / flagboxes: host arrays of `world` device pointers as mapped in THIS process (own at
+ * [rank]); a flag box is a zero-initialised uaps_xchg_alloc mailbox used only for this purpose.  The other arguments are
+ * those of uaps_adam_step.  n must be a multiple of 4.  Waits are bounded by UAPS_XCHG_TIMEOUT_MS (default 30000): on a
+ * time-out the update is skipped and word 81 of the own flag box latches the epoch. */
+int uaps_peer_alloc(void** ptr, size_t bytes);
+int uaps_peer_free(void* ptr);
+int uaps_grad_reduce_adam(float* p, const float* const* grads, float* m, float* v, int64_t n,
+                          void* const* flagboxes, int rank, int world, int64_t step, float lr, float beta1,
+                          float beta2, float eps, float grad_scale, UapsStepState* state, const float* guard,
+                          cudaStream_t stream);
+
 /* On-device confusion matrix behind utilities/metrics.py (pixel_accuracy :8, mIoU :16, mDice :40):
  * conf[label * C + argmax(softmax(logits))] += 1 per pixel (labels outside [0,C) ignored).  logits [B,C,HW] fp32,
  * labels [B,HW] int64, conf C*C uint64 ACCUMULATED into. */

@@ -189,3 +189,114 @@ def test_two_processes_peer_exchange_matches_nccl_and_single():
         np.testing.assert_allclose([l0, p0, u0], [l1, p1, u1], rtol=1e-6)
         np.testing.assert_allclose([l0, p0, u0], [loss.item(), ps.item(), unc.item()], rtol=2e-6)
     assert out[0][0][2:5] == out[1][0][2:5]                  # both ranks: identical scalars
+
+
+# ---- two processes: a sharded TRAINING ITERATION equals the reference's DataParallel semantics ------------------------
+def _train_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from oracle.unet_ref import feature_shapes, synthetic_rand, synthetic_state_dict
+        from uaps_b200.train import UAPSConfig, UAPSTrainer
+        from uaps_b200.unet import UNet_UAPS
+        torch.backends.cudnn.allow_tf32 = False
+        Bs, Hh, Cc = 2, 64, 4
+        # (a) fp32 reference-precision path, every draw injected: must equal the single-process emulation
+        model = UNet_UAPS(3, Cc, compute="fp32")
+        model.load_state_dict(synthetic_state_dict(3, Cc, seed=11 + 7 * rank))     # ranks start DIFFERENT on purpose ...
+        model = model.to(dev)
+        tr = UAPSTrainer(model, UAPSConfig(num_classes=Cc), group=dist.group.WORLD)   # ... the constructor broadcasts rank 0's
+        g = torch.Generator().manual_seed(2)
+        xl, xu = torch.randn(world * Bs, 3, Hh, Hh, generator=g), torch.randn(world * Bs, 3, Hh, Hh, generator=g)
+        yl = torch.randint(0, Cc, (world * Bs, Hh, Hh), generator=g)
+        sl = slice(rank * Bs, (rank + 1) * Bs)
+        to = lambda r: {k: [v.to(dev) if torch.is_tensor(v) else v for v in vals] for k, vals in r.items()}
+        rl, ru = to(synthetic_rand(feature_shapes(Bs, Hh, Hh), 1 + rank)), to(synthetic_rand(feature_shapes(Bs, Hh, Hh), 5 + rank))
+        out = tr.step(xl[sl].to(dev), yl[sl].to(dev), xu[sl].to(dev), mix_w=MIX, rand_l=rl, rand_u=ru)
+        flat = tr.optimizer.flat_p.detach().cpu()
+        # (b) bf16 captured path: replicas stay bit-identical and the loss falls
+        torch.manual_seed(100 + rank)                                          # different initial weights per rank again
+        m16 = UNet_UAPS(3, Cc).to(dev)
+        t16 = UAPSTrainer(m16, UAPSConfig(num_classes=Cc, graph_warmup=1), group=dist.group.WORLD)
+        yb = ((xl[sl, 0] > 0).long() + 2 * (xl[sl, 1] > 0).long()).to(dev)
+        losses = [float(t16.step(xl[sl].to(dev), yb, xu[sl].to(dev))["loss"]) for _ in range(8)]
+        q.put((rank, float(out["loss"]), flat, losses, t16.optimizer.flat_p.detach().cpu(), len(t16._graphs), t16.state is not None,
+               t16.skipped_steps()))
+    finally:
+        from uaps_b200 import comm
+        comm.close_all()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_training_iteration_matches_dataparallel_semantics():
+    """Reference semantics (nn.DataParallel, UAPS_model.py:13): each replica runs the network on its shard with its OWN
+    BatchNorm statistics, the logits are gathered and the losses (CE / Dice / mean exp(-KL)) are taken over the WHOLE batch,
+    gradients are summed.  Emulated here in one process with the same injected draws and compared with two real ranks."""
+    import torch.multiprocessing as mp
+    from oracle.unet_ref import feature_shapes, synthetic_rand, synthetic_state_dict
+    from uaps_b200.losses import uaps_supervised_loss, uaps_unlabeled_loss
+    from uaps_b200.train import FlatAdam, FlatGradBuffer
+    from uaps_b200.unet import UNet_UAPS
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in procs:
+        r = q.get(timeout=600)
+        got[r[0]] = r[1:]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    # single-process emulation on GPU 0
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.allow_tf32 = False
+    world, Bs, Hh, Cc = 2, 2, 64, 4
+    model = UNet_UAPS(3, Cc, compute="fp32")
+    model.load_state_dict(synthetic_state_dict(3, Cc, seed=11))            # rank 0's weights (what the broadcast distributes)
+    model = model.to(dev).train()
+    buf = FlatGradBuffer(model.parameters())
+    opt = FlatAdam(buf, lr=1e-3)
+    g = torch.Generator().manual_seed(2)
+    xl, xu = torch.randn(world * Bs, 3, Hh, Hh, generator=g), torch.randn(world * Bs, 3, Hh, Hh, generator=g)
+    yl = torch.randint(0, Cc, (world * Bs, Hh, Hh), generator=g)
+    to = lambda r: {k: [v.to(dev) if torch.is_tensor(v) else v for v in vals] for k, vals in r.items()}
+    outs_l, outs_u = [], []
+    for r in range(world):
+        sl = slice(r * Bs, (r + 1) * Bs)
+        rl, ru = to(synthetic_rand(feature_shapes(Bs, Hh, Hh), 1 + r)), to(synthetic_rand(feature_shapes(Bs, Hh, Hh), 5 + r))
+        outs_l.append(model(xl[sl].to(dev), rand=rl))
+        outs_u.append(model(xu[sl].to(dev), rand=ru))
+    cat = lambda outs: [torch.cat([o[k] for o in outs], 0) for k in range(4)]
+    sup = uaps_supervised_loss(cat(outs_l), yl.to(dev))[0]
+    from uaps_b200.ramps import get_current_consistency_weight
+    cw = get_current_consistency_weight(0, 0.1, 200.0, 80)
+    lu = uaps_unlabeled_loss(cat(outs_u), MIX, cw, cw)[0]
+    loss = sup + lu
+    buf.zero()
+    loss.backward()
+    opt.step()
+    ref_flat = opt.flat_p.detach().cpu()
+    for rank in (0, 1):
+        loss_r, flat_r, losses16, flat16, ngraphs, dev_mode, skipped = got[rank]
+        assert loss_r == pytest.approx(float(loss), rel=1e-5)
+        # Adam normalises the gradient: compare the update direction of every parameter element that moved
+        assert dev_mode and ngraphs == 1 and skipped == 0
+        assert all(np.isfinite(losses16)) and losses16[-1] < losses16[0], losses16
+    assert torch.equal(got[0][1], got[1][1]), "fp32 path: replicas diverged"
+    assert torch.equal(got[0][4], got[1][4]), "bf16 captured path: replicas diverged"
+    assert got[0][3] == got[1][3], "both ranks must log the same (global) loss"
+    # parameters after one step vs the emulation: same update sign on > 99.5 % of the elements that moved, and close in value
+    torch.testing.assert_close(got[0][1], ref_flat, rtol=0, atol=2.5e-3)           # |update| <= lr = 1e-3 per element
+    m0 = UNet_UAPS(3, Cc, compute="fp32"); m0.load_state_dict(synthetic_state_dict(3, Cc, seed=11)); m0 = m0.to(dev)
+    start = FlatAdam(FlatGradBuffer(m0.parameters()), lr=1e-3).flat_p.detach().cpu()
+    du_ref, du_got = ref_flat - start, got[0][1] - start
+    live = du_ref.abs() > 5e-4                                                  # elements with a clear (non-noise) gradient
+    agree = (torch.sign(du_ref[live]) == torch.sign(du_got[live])).float().mean().item()
+    assert agree > 0.995, agree

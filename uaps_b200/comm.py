@@ -86,6 +86,113 @@ class LossExchange:
                 self.own = None
 
 
+class PeerRegion:
+    """`nbytes` of zero-filled device memory on every rank of `group`, each mapped into every other rank (CUDA IPC).
+    ``ptrs[r]`` is rank r's buffer as seen from this process (own at ``ptrs[rank]``).  COLLECTIVE constructor; raises
+    on every rank together if any rank could not allocate / export / map."""
+
+    def __init__(self, group, device: torch.device, nbytes: int):
+        self.world, self.rank, self.device, self.nbytes = dist.get_world_size(group), dist.get_rank(group), device, int(nbytes)
+        lib = L.lib()
+        self.own, self._opened, self.ptrs = None, [], (C.c_void_p * self.world)()
+        with torch.cuda.device(device):
+            mine, own = None, C.c_void_p()
+            if lib.uaps_peer_alloc(C.byref(own), self.nbytes) == 0:
+                self.own = own.value
+                handle = C.create_string_buffer(64)
+                if lib.uaps_xchg_export(self.own, handle) == 0:
+                    mine = bytes(handle.raw)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            failed = any(h is None for h in handles)
+            if not failed:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self.ptrs[r] = self.own
+                        continue
+                    p = C.c_void_p()
+                    if lib.uaps_xchg_import(C.create_string_buffer(h, 64), C.byref(p)) != 0:
+                        failed = True
+                        break
+                    self.ptrs[r] = p.value
+                    self._opened.append(p.value)
+            outcomes = [None] * self.world
+            dist.all_gather_object(outcomes, failed, group=group)        # agree on the outcome; also: everything is mapped
+        if any(outcomes):
+            self.close()
+            raise RuntimeError("could not allocate / export / map a peer region (CUDA IPC or peer access unavailable)")
+
+    def tensor(self, dtype=torch.float32) -> torch.Tensor:
+        """The own buffer as a torch tensor (no copy; this object keeps the allocation alive and must outlive the tensor)."""
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+        region = self
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (region.nbytes // itemsize,), "typestr": typestr, "data": (region.own, False),
+                                        "version": 2, "strides": None}
+        holder = _Arr()
+        t = torch.as_tensor(holder, device=self.device)
+        t._uaps_region = self                      # keep the allocation alive as long as the tensor object lives
+        return t
+
+    def close(self) -> None:
+        lib = L.lib()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in getattr(self, "_opened", []):
+                lib.uaps_xchg_close(p)
+            self._opened = []
+            if self.own:
+                lib.uaps_peer_free(self.own)
+                self.own = None
+
+
+class PeerGradReducer:
+    """Host half of ``uaps_grad_reduce_adam``: a peer-mapped flat gradient buffer of `numel` floats on every rank plus the
+    flag boxes of the two barriers.  ``UAPSTrainer`` builds its ``FlatGradBuffer`` on ``grad_tensor()`` so that the
+    backward kernels write the gradients straight into memory the peers can read."""
+
+    def __init__(self, group, device: torch.device, numel: int):
+        self.grads = PeerRegion(group, device, 4 * int(numel))
+        self.flags = PeerRegion(group, device, L.lib().uaps_xchg_mailbox_bytes())
+        self.rank, self.world, self.numel = self.grads.rank, self.grads.world, int(numel)
+
+    def grad_tensor(self) -> torch.Tensor:
+        return self.grads.tensor(torch.float32)
+
+    def status(self) -> int:
+        """0, or the epoch of the first reduce that timed out waiting for a peer (synchronises)."""
+        return int(self.flags.tensor(torch.int32)[81].item())
+
+    def close(self) -> None:
+        self.grads.close()
+        self.flags.close()
+
+
+def new_grad_reducer(group, device: torch.device, numel: int) -> Optional[PeerGradReducer]:
+    """COLLECTIVE.  None when peer memory cannot be used (same conditions as ``new_exchange``)."""
+    if not dist.is_initialized():
+        return None
+    ok = (os.environ.get("UAPS_GRAD_REDUCE", "peer") != "nccl" and dist.get_backend(group) == "nccl"
+          and 1 < dist.get_world_size(group) <= MAX_RANKS)
+    if ok:
+        hosts = [None] * dist.get_world_size(group)
+        dist.all_gather_object(hosts, socket.gethostname(), group=group)
+        ok = len(set(hosts)) == 1
+    if not ok:
+        return None
+    try:
+        red = PeerGradReducer(group, device, numel)
+    except RuntimeError as e:               # raised on every rank together (PeerRegion agrees on the outcome collectively)
+        if dist.get_rank(group) == 0:
+            import warnings
+            warnings.warn(f"uaps_b200: peer-memory gradient reduce unavailable, using the NCCL all-reduce: {e}")
+        return None
+    _owned.append(red)
+    return red
+
+
 _exchanges: Dict[tuple, Optional[LossExchange]] = {}
 _owned = []
 

@@ -68,13 +68,25 @@ class FlatGradBuffer:
 
     ALIGN = 64                            # elements: every parameter starts on a 256-byte boundary, like a torch allocation
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
-        self.offsets, n = [], 0
-        for p in self.params:
-            self.offsets.append(n)
-            n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+    @classmethod
+    def layout(cls, params):
+        """(trainable parameters, their element offsets, total padded element count) of the flat layout."""
+        params = [p for p in params if p.requires_grad]
+        offsets, n = [], 0
+        for p in params:
+            offsets.append(n)
+            n += (p.numel() + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
+        return params, offsets, n
+
+    def __init__(self, params, flat: Optional[torch.Tensor] = None):
+        """flat: an existing zero-filled fp32 buffer of the layout's size to use instead of a fresh one -- at N > 1 the
+        peer-mapped allocation of ``comm.PeerGradReducer``, so the backward kernels write where the peers can read."""
+        self.params, self.offsets, n = self.layout(params)
+        if flat is None:
+            flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        elif flat.numel() != n or flat.dtype != torch.float32:
+            raise RuntimeError("flat gradient buffer has the wrong size / dtype")
+        self.flat = flat
         for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
 
@@ -147,10 +159,12 @@ class FlatAdam(torch.optim.Optimizer):
             self._lr_on_device = self.lr
 
     @torch.no_grad()
-    def step(self, closure=None, guard: Optional[torch.Tensor] = None, use_device_state: bool = False):
+    def step(self, closure=None, guard: Optional[torch.Tensor] = None, use_device_state: bool = False, reducer=None):
         """One Adam update.  use_device_state: bias corrections / lr from the attached device state (the caller has run
         ``uaps_step_begin`` this iteration); ``guard`` (a device scalar, the loss) then skips the update when it is not
-        finite.  Otherwise the host step count is used, as torch.optim.Adam does."""
+        finite.  Otherwise the host step count is used, as torch.optim.Adam does.
+        reducer (``comm.PeerGradReducer``, N > 1): the SAME launch first sums every rank's gradients over NVLink peer
+        memory (uaps_grad_reduce_adam) -- the gradients must then NOT have been all-reduced already."""
         from . import _lib as L
         if closure is not None:
             raise RuntimeError("FlatAdam.step does not take a closure")
@@ -162,6 +176,13 @@ class FlatAdam(torch.optim.Optimizer):
             step, gptr = 1, (None if guard is None else guard.data_ptr())
         g = self.param_groups[0]
         with L.on_device(self.flat_p.device):
+            if reducer is not None:
+                L.check(L.lib().uaps_grad_reduce_adam(self.flat_p.data_ptr(), reducer.grads.ptrs, self.exp_avg.data_ptr(),
+                                                      self.exp_avg_sq.data_ptr(), self.flat_p.numel(), reducer.flags.ptrs,
+                                                      reducer.rank, reducer.world, step, float(g["lr"]), self.betas[0],
+                                                      self.betas[1], self.eps, 1.0, None if st is None else st.base, gptr,
+                                                      L.stream_ptr()), "uaps_grad_reduce_adam")
+                return
             L.check(L.lib().uaps_adam_step(self.flat_p.data_ptr(), self.grads.flat.data_ptr(), self.exp_avg.data_ptr(),
                                            self.exp_avg_sq.data_ptr(), self.flat_p.numel(), step, float(g["lr"]),
                                            self.betas[0], self.betas[1], self.eps, 1.0,
@@ -222,7 +243,14 @@ class UAPSTrainer:
         self.model, self.cfg, self.group = model, cfg or UAPSConfig(), group
         self.world = dist.get_world_size(group) if (group is not None and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
-        self.grads = FlatGradBuffer(model.parameters())
+        # N > 1: the flat gradient buffer lives in peer-mapped memory and ONE kernel sums all ranks' gradients over NVLink
+        # and applies Adam (comm.PeerGradReducer / uaps_grad_reduce_adam); NCCL's all-reduce is only the fallback
+        self.reducer = None
+        params, _, numel = FlatGradBuffer.layout(model.parameters())
+        if self.world > 1 and self.cfg.optimizer != "torch" and params[0].is_cuda:
+            from .comm import new_grad_reducer
+            self.reducer = new_grad_reducer(group, params[0].device, numel)       # collective
+        self.grads = FlatGradBuffer(model.parameters(), flat=None if self.reducer is None else self.reducer.grad_tensor())
         if self.cfg.optimizer == "torch":
             self.optimizer = torch.optim.Adam(self.grads.params, lr=self.cfg.base_lr, fused=True)   # :112 (library kernel)
         else:
@@ -287,7 +315,8 @@ class UAPSTrainer:
         injected = mix_w is not None or rand_l is not None or rand_u is not None
         if self.state is None or injected:
             return self._host_step(x_l, y_l, x_u, mix_w, rand_l, rand_u)
-        if not self.cfg.cuda_graph:
+        if not self.cfg.cuda_graph or (self.world > 1 and self.reducer is None):
+            # (an NCCL all-reduce inside the iteration is not captured: only the all-kernel iteration is)
             out = self._device_step(x_l, y_l, x_u)
             self._iter += 1
             return out
@@ -321,7 +350,8 @@ class UAPSTrainer:
         return cap
 
     def _reduce_gradients(self) -> None:
-        self.grads.all_reduce_sum(self.group)
+        if self.reducer is None:                 # with a reducer the sum happens inside the optimizer kernel
+            self.grads.all_reduce_sum(self.group)
 
     def _device_step(self, x_l, y_l, x_u) -> Dict[str, torch.Tensor]:
         """The iteration with every per-iteration scalar in device memory: a static launch sequence."""
@@ -340,7 +370,7 @@ class UAPSTrainer:
             loss.backward()                                                                      # :287
         self._reduce_gradients()
         # a non-finite loss (an exchange that timed out on a dead peer) must not reach the parameters: the kernel skips
-        self.optimizer.step(guard=loss.detach(), use_device_state=True)                          # :292
+        self.optimizer.step(guard=loss.detach(), use_device_state=True, reducer=self.reducer)    # :292
         return {"loss": loss.detach(), "supervised_loss": sup.detach(), "total_loss_ce": tce.detach(),
                 "total_loss_dice": tdice.detach(), "ps_loss": ps_loss.detach(), "l_uncert": l_unc.detach(),
                 "loss_ce_k": ce_k}
@@ -359,9 +389,11 @@ class UAPSTrainer:
             self.grads.zero()                                                                    # :285
             loss.backward()                                                                      # :287
         self._reduce_gradients()
-        if self.world > 1 and not bool(torch.isfinite(loss.detach())):
+        if self.world > 1 and self.reducer is None and not bool(torch.isfinite(loss.detach())):
             # an exchange that timed out yields NaN scalars on every rank: skip the update instead of poisoning the replicas
             warnings.warn("uaps_b200: non-finite loss (loss-sum exchange timed out?); optimizer step skipped")
+        elif self.reducer is not None:
+            self.optimizer.step(reducer=self.reducer)            # sums the ranks' gradients and updates, one kernel
         else:
             self.optimizer.step()                                                                # :292
         self.iter_num = self._iter + 1
