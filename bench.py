@@ -418,7 +418,7 @@ def sharded_equals_full(dev, group, world, rank):
         full.append(torch.cat(parts, 0).requires_grad_(True))
     lf, pf, uf, pseudo_f, _ = uaps_unlabeled_loss(full, mix_w, CW1, CW2, group=None, return_pseudo=True)
     lf.backward()
-    rel = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
+    rel = lambda a, b: abs(float(a.detach()) - float(b.detach())) / max(abs(float(b.detach())), 1e-30)
     errs = [rel(loss, lf), rel(ps, pf), rel(unc, uf)]
     sl = slice(rank * B, (rank + 1) * B)
     gerr = max(float((a.grad - b.grad[sl]).abs().max() / b.grad[sl].abs().max()) for a, b in zip(z, full))
