@@ -448,8 +448,9 @@ def train_step_bench(c, dev, group, world, rank, steps: int = 8, warmup: int = 4
     loss_h = torch.empty((), dtype=torch.float32).pin_memory()
 
     def it():
-        xl, xu, yl = xl_h.to(dev, non_blocking=True), xu_h.to(dev, non_blocking=True), yl_h.to(dev, non_blocking=True)
-        out = trainer.step(xl, yl, xu)
+        # pinned host batch in (H2D on the trainer's copy stream, overlapping the previous iteration's kernels),
+        # loss scalar out (D2H) -- both inside the timed region, every step
+        out = trainer.step_host(xl_h, yl_h, xu_h)
         loss_h.copy_(out["loss"], non_blocking=True)
 
     for _ in range(warmup):

@@ -257,3 +257,23 @@ def test_k5_and_dataset_shapes_run_on_the_kernel_path(shape):
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
     outs = model(xu)
     assert len(outs) == n_aux + 1 and all(o.shape == (B, C, H, W) and o.dtype == torch.float32 for o in outs)
+
+
+def test_step_host_prefetch_matches_step():
+    """step_host (pinned host batch, H2D on a side stream into double-buffered staging) runs the same iteration as step."""
+    from uaps_b200.train import UAPSConfig, UAPSTrainer
+    from uaps_b200.unet import UNet_UAPS
+    dev = torch.device("cuda:0")
+    batches = [tuple(t.cpu().pin_memory() for t in _fixed_batch(dev, B=2, HW=64, seed=s)) for s in range(3)]
+    curves = {}
+    for host in (False, True):
+        torch.manual_seed(0)
+        tr = UAPSTrainer(UNet_UAPS(3, 4).to(dev), UAPSConfig(graph_warmup=1))
+        out = []
+        for i in range(9):
+            b = batches[i % 3]
+            o = tr.step_host(*b) if host else tr.step(*(t.to(dev) for t in b))
+            out.append(float(o["loss"]))
+        curves[host] = out
+    for s, (u, v) in enumerate(zip(curves[False], curves[True])):
+        assert math.isfinite(v) and abs(u - v) <= 0.03 * abs(u), (s, curves)

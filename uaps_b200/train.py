@@ -338,6 +338,36 @@ class UAPSTrainer:
         self._iter += 1
         return cap.out
 
+    def step_host(self, x_l: torch.Tensor, y_l: torch.Tensor, x_u: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """``step`` fed from (pinned) HOST tensors, as a data loader delivers them (UAPS_train.py:160-168 moves each batch with
+        ``.cuda()`` and waits for it).  The H2D copies run on a side stream into one of two staging sets, so the copy of
+        batch i+1 overlaps the kernels of batch i (the host runs ahead of the device: ``step`` only enqueues work)."""
+        dev = self.grads.flat.device
+        if not hasattr(self, "_h2d_stream"):
+            self._h2d_stream, self._stage, self._stage_free, self._stage_i = torch.cuda.Stream(dev), {}, {}, 0
+        main = torch.cuda.current_stream(dev)
+        slot = self._stage_i & 1
+        self._stage_i += 1
+        key = (slot, tuple(x_l.shape), tuple(y_l.shape), tuple(x_u.shape), x_l.dtype, y_l.dtype)
+        bufs = self._stage.get(key)
+        if bufs is None:
+            bufs = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in (x_l, y_l, x_u))
+            self._stage[key] = bufs
+        with torch.cuda.stream(self._h2d_stream):
+            free = self._stage_free.get(slot)
+            if free is not None:
+                self._h2d_stream.wait_event(free)             # the iteration that last read this staging set has consumed it
+            for d, h in zip(bufs, (x_l, y_l, x_u)):
+                d.copy_(h, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._h2d_stream)
+        main.wait_event(ready)
+        out = self.step(*bufs)
+        done = torch.cuda.Event()
+        done.record(main)
+        self._stage_free[slot] = done
+        return out
+
     def _capture(self, key, x_l, y_l, x_u) -> _Captured:
         cap = _Captured()
         cap.x_l, cap.y_l, cap.x_u = torch.empty_like(x_l), torch.empty_like(y_l), torch.empty_like(x_u)
