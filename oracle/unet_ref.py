@@ -154,3 +154,67 @@ def synthetic_rand(feat_shapes: Sequence[tuple], seed: int = 99) -> Dict[str, li
 
 def feature_shapes(B: int, H: int, W: int):
     return [(B, c, H >> l, W >> l) for l, c in enumerate(FT_CHNS)]
+
+
+def unet_layer_trace(x: torch.Tensor, sd: Dict[str, torch.Tensor], rand: Dict[str, list], decoders: Sequence[str] = DECODERS):
+    """The forward of ``unet_uaps_ref`` once more, recording every primitive layer as a dict
+    {name, kind, inputs, out, ...} with ``retain_grad`` on every tensor, for TEACHER-FORCED per-layer parity tests: each
+    hand-written layer of the product is fed the oracle's own input activations (and, backward, the oracle's own upstream
+    gradient) and compared with the oracle's output, so rounding does not compound through the 22-layer network.
+    kinds: conv (inputs 1 or 2 = the torch.cat halves, :85), bn_act (BatchNorm(train) + LeakyReLU, pre-dropout),
+    maxpool, upsample, logits (out_conv)."""
+    trace = []
+
+    def keep(t):
+        if t.requires_grad:
+            t.retain_grad()
+        return t
+
+    def rec(**kw):
+        trace.append(kw)
+        return kw["out"]
+
+    def block(inputs, prefix, p_drop, keep_mask):
+        cc = prefix + ".conv_conv"
+        xin = inputs[0] if len(inputs) == 1 else torch.cat(list(inputs), dim=1)
+        y = keep(F.conv2d(xin, sd[cc + ".0.weight"], sd[cc + ".0.bias"], padding=1))
+        rec(name=cc + ".0", kind="conv", inputs=list(inputs), out=y, weight=cc + ".0.weight", bias=cc + ".0.bias", before_bn=True)
+        a = keep(F.leaky_relu(_bn_train(y, sd, cc + ".1", None), 0.01))
+        rec(name=cc + ".1", kind="bn_act", inputs=[y], out=a, bn=cc + ".1")
+        if p_drop > 0.0:
+            a = keep(dropout_ref(a, keep_mask, p_drop))
+        y2 = keep(F.conv2d(a, sd[cc + ".4.weight"], sd[cc + ".4.bias"], padding=1))
+        rec(name=cc + ".4", kind="conv", inputs=[a], out=y2, weight=cc + ".4.weight", bias=cc + ".4.bias", before_bn=True)
+        a2 = keep(F.leaky_relu(_bn_train(y2, sd, cc + ".5", None), 0.01))
+        rec(name=cc + ".5", kind="bn_act", inputs=[y2], out=a2, bn=cc + ".5")
+        return a2
+
+    feats, cur = [], keep(x)
+    for lvl in range(5):
+        if lvl > 0:
+            pooled = keep(F.max_pool2d(cur, 2))
+            rec(name=f"pool{lvl}", kind="maxpool", inputs=[cur], out=pooled)
+            cur = pooled
+        cur = block([cur], ENC_PREFIX[lvl], ENC_DROPOUT[lvl], rand["enc_keep"][lvl])
+        feats.append(cur)
+    per_dec = {"main_decoder": feats,
+               "aux_decoder1": [keep(feature_noise_ref(f, n)) for f, n in zip(feats, rand["noise"])],
+               "aux_decoder2": [keep(dropout_ref(f, m, 0.5)) for f, m in zip(feats, rand["aux2_keep"])],
+               "aux_decoder3": [keep(feature_dropout_ref(f, u)) for f, u in zip(feats, rand["u"])]}
+    outs = []
+    for name in decoders:
+        fs = per_dec[name]
+        cur = fs[4]
+        for i, skip in zip((1, 2, 3, 4), (fs[3], fs[2], fs[1], fs[0])):
+            up = f"{name}.up{i}"
+            y = keep(F.conv2d(cur, sd[up + ".conv1x1.weight"], sd[up + ".conv1x1.bias"]))
+            rec(name=up + ".conv1x1", kind="conv", inputs=[cur], out=y, weight=up + ".conv1x1.weight", bias=up + ".conv1x1.bias",
+                before_bn=False)
+            u2 = keep(F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True))
+            rec(name=up + ".upsample", kind="upsample", inputs=[y], out=u2)
+            cur = block([skip, u2], up + ".conv", 0.0, None)
+        z = keep(F.conv2d(cur, sd[name + ".out_conv.weight"], sd[name + ".out_conv.bias"], padding=1))
+        rec(name=name + ".out_conv", kind="logits", inputs=[cur], out=z, weight=name + ".out_conv.weight",
+            bias=name + ".out_conv.bias", before_bn=False)
+        outs.append(z)
+    return outs, trace
