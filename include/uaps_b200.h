@@ -321,10 +321,17 @@ int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, int c2_st
 /* Weight gradient on tcgen05 (MN-major operands straight from the channels-last tensors):
  * dw[co][ci_offset + ci][r][s] += sum_pixels dy[p][co] * x[p + (r-1, s-1)][ci].  dw is fp32 in torch layout
  * [cout][cin_total][ks][ks] and is ACCUMULATED into (zero it first); a concatenated input is two calls
- * with different ci_offset.  cin must be a multiple of 16 (pad the 3-channel network input). */
+ * with different ci_offset.  cin must be a multiple of 16 (pad the 3-channel network input).
+ * workspace (nullable): deterministic split-K.  The pixel dimension is split over CTAs; without a workspace their partial
+ * sums meet in dw through fp32 atomics (cout*cin*ks*ks of them per split: half the kernel's time on the 64..256-channel
+ * layers, and a run-to-run rounding order).  With >= uaps_conv_wgrad_workspace_bytes of 16-byte-aligned scratch whose first
+ * 256 bytes are zero before the first use (every launch leaves them zero), the CTAs store their partials, meet at a grid
+ * barrier (the launch is one co-resident wave) and fold them in split order: no atomics, bit-reproducible.  The same
+ * scratch can serve every call of a stream (the fold ends inside the launch). */
+size_t uaps_conv_wgrad_workspace_bytes(int B, int H, int W, int cout, int cin, int ks);
 int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int x_c_stride, float* dw,
                     int B, int H, int W, int cout, int cin, int cin_total, int ci_offset, int ks,
-                    cudaStream_t stream);
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- optimizer (UAPS_train.py:112, 292: torch.optim.Adam(model.parameters(), lr) and its step()) -----------------
  * One Adam step over flat fp32 buffers of n elements (parameters, gradients, first and second moments; 16-byte

@@ -183,3 +183,31 @@ def test_pixel_folded_variants():
     refl = _ref(x, wl, bl, 3)
     outl = PackedConv(wl, bl, fold=4)(to_nhwc_bf16(x), out_nchw_f32=True)
     assert outl.shape == refl.shape and (outl - refl).abs().max().item() <= 2e-3 * refl.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 64, 16, 16, 3), (2, 32, 32, 128, 128, 3), (3, 16, 16, 256, 256, 3), (2, 64, 64, 64, 32, 1),
+                                   (2, 48, 80, 32, 64, 3), (8, 128, 128, 16, 4, 3)])
+def test_wgrad_deterministic_split_k(shape):
+    """Deterministic split-K (workspace + in-launch fold, no atomics): bit-reproducible, equal to the atomic path up to
+    fp32 re-association, accumulates into an existing gradient, and reuses one workspace across layers."""
+    from uaps_b200.conv import conv_wgrad
+    B, H, W, cin, cout, ks = shape
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(B * H + cin)
+    x = torch.randn(B, H, W, cin, generator=g, device=dev).to(torch.bfloat16)
+    cop = (cout + 15) // 16 * 16
+    dy = torch.randn(B, H, W, cop, generator=g, device=dev).to(torch.bfloat16)
+    dy[..., cout:] = 0
+    a = conv_wgrad(dy, [x], cout, cin, ks, deterministic=True)
+    b = conv_wgrad(dy, [x], cout, cin, ks, deterministic=True)
+    assert torch.equal(a, b), "deterministic split-K must be bit-reproducible"
+    c = conv_wgrad(dy, [x], cout, cin, ks, deterministic=False)
+    torch.testing.assert_close(a, c, rtol=1e-4, atol=1e-4 * c.abs().max().item())
+    # fp32 reference on the same bf16 operands
+    xr, dyr = x.float().permute(0, 3, 1, 2), dy[..., :cout].float().permute(0, 3, 1, 2)
+    w = torch.zeros(cout, cin, ks, ks, device=dev, requires_grad=True)
+    (torch.nn.functional.conv2d(xr, w, padding=ks // 2) * dyr).sum().backward()
+    assert (a - w.grad).abs().max().item() <= 2e-3 * w.grad.abs().max().item() + 1e-5
+    base = torch.full_like(a, 0.5)                       # accumulates into what is there
+    conv_wgrad(dy, [x], cout, cin, ks, out=base, deterministic=True)
+    torch.testing.assert_close(base, a + 0.5, rtol=1e-6, atol=1e-6)

@@ -128,18 +128,49 @@ class PackedConv:
         return out if not split else (out, out2)
 
 
-def conv_wgrad(dy_nhwc: torch.Tensor, xs, cout: int, cin_total: int, ks: int, out: torch.Tensor = None) -> torch.Tensor:
+_wgrad_ws = {}
+_WGRAD_WS_MIN = 64 << 20
+_WGRAD_DETERMINISTIC = os.environ.get("UAPS_WGRAD_ATOMIC") is None
+
+
+def _wgrad_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Scratch of the deterministic split-K weight gradient: ONE buffer per (device, stream) serves every layer (the fold
+    of the partial sums ends inside the launch, and launches of a stream are ordered).  The kernel's barrier counters live
+    in its first 256 bytes: zeroed at allocation, and every launch leaves them zero."""
+    key = (device.index, L.stream_ptr())
+    ws = _wgrad_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), _WGRAD_WS_MIN), dtype=torch.uint8, device=device)
+        ws[:256].zero_()                              # only the barrier counters need to start at zero
+        if len(_wgrad_ws) >= 8:
+            _wgrad_ws.pop(next(iter(_wgrad_ws)))
+        _wgrad_ws[key] = ws
+    return ws
+
+
+def conv_wgrad(dy_nhwc: torch.Tensor, xs, cout: int, cin_total: int, ks: int, out: torch.Tensor = None,
+               deterministic: bool = None) -> torch.Tensor:
     """dW (fp32, torch layout [cout][cin_total][ks][ks]) of a conv whose input is the channel concat of `xs`
     (NHWC bf16 tensors, each a multiple of 16 channels) and whose output gradient is dy_nhwc.  `out`: an fp32
-    tensor of that shape to ACCUMULATE into (e.g. the parameter's pre-zeroed .grad) instead of a fresh one."""
+    tensor of that shape to ACCUMULATE into (e.g. the parameter's pre-zeroed .grad) instead of a fresh one.
+    deterministic (default on; UAPS_WGRAD_ATOMIC=1 turns it off): split-K partial sums go through a workspace and are
+    folded in a fixed order inside the launch instead of meeting in dW through fp32 atomics."""
     B, H, W, dcs = dy_nhwc.shape
     dw = out if out is not None else torch.zeros((cout, cin_total, ks, ks), dtype=torch.float32, device=dy_nhwc.device)
     off = 0
+    det = _WGRAD_DETERMINISTIC if deterministic is None else deterministic
+    lib = L.lib()
     with L.on_device(dy_nhwc.device):
         for x in xs:
             c = x.shape[3]
-            L.check(L.lib().uaps_conv_wgrad(dy_nhwc.data_ptr(), dcs, x.data_ptr(), c, dw.data_ptr(), B, H, W, cout, c,
-                                            cin_total, off, ks, L.stream_ptr()), "uaps_conv_wgrad")
+            ws, ws_ptr, ws_n = None, None, 0
+            if det:
+                need = lib.uaps_conv_wgrad_workspace_bytes(B, H, W, cout, c, ks)
+                if need:
+                    ws = _wgrad_workspace(dy_nhwc.device, need)
+                    ws_ptr, ws_n = ws.data_ptr(), ws.numel()
+            L.check(lib.uaps_conv_wgrad(dy_nhwc.data_ptr(), dcs, x.data_ptr(), c, dw.data_ptr(), B, H, W, cout, c,
+                                        cin_total, off, ks, ws_ptr, ws_n, L.stream_ptr()), "uaps_conv_wgrad")
             off += c
     return dw
 

@@ -43,7 +43,13 @@ struct WgradArgs {
     int m_rows;                                    // MMA M: 64 when the taps x channel-chunk rows fit (halves the A-operand fetch), else 128
     int stages;                                    // depth of the TMA -> MMA ring (3..8)
     int fused_r;                                   // 1: the vertical taps ride in N (dY box with a row halo), one MMA per k-step
+    // deterministic split-K (workspace given): every CTA stores its partial accumulators, the grid meets at a barrier and
+    // each CTA then folds a slice of the output over all splits in split order and adds it to dW -- no fp32 atomics
+    unsigned* ws_counters;                         // [0] arrivals, [1] departures (self-resetting; zero before the first use)
+    float* ws_partials;                            // [split][group][r block][row][n_co]
+    int groups;                                    // n_chunks * m_tiles
 };
+constexpr size_t WS_HEADER = 256;
 
 // MN-major descriptors (cute::UMMA canonical forms, units of 16 bytes):
 //   SW128: ((8,n),(8,k)):((1,LBO),(8,SBO))   SW64: ((4,n),(8,k)):((1,LBO),(4,SBO))   SW32: ((2,n),(8,k)):((1,LBO),(2,SBO))
@@ -188,6 +194,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const int row = a.m_rows == 64 ? warp * 16 + lane : warp * 32 + lane;
         const int s_tap = row / a.n_chunk, ci = a.ci_offset + nc * a.n_chunk + row % a.n_chunk;
         const bool lane_ok = row < a.ks * a.n_chunk && (a.m_rows == 128 || lane < 16);
+        if (a.ws_partials != nullptr) {
+            // ---- deterministic split-K, part 1: this CTA's partial accumulators -> workspace (plain 16-byte stores) ----
+            const int rows = a.ks * a.n_chunk;
+            const size_t blk_elems = (size_t)a.ks * rows * n_co;
+            float* P = a.ws_partials + ((size_t)split * a.groups + (size_t)nc * gridDim.z + mt) * blk_elems;
+            for (int blk = 0; blk < a.ks; ++blk)
+                for (int j = 0; j < n_co / 16; ++j) {
+                    float v[16];
+                    tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + blk * n_co + j * 16, v);
+                    if (lane_ok) {
+                        float4* dst = reinterpret_cast<float4*>(P + ((size_t)blk * rows + row) * n_co + j * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+        } else
         for (int blk = 0; blk < a.ks; ++blk) {
             // accumulator column block: per-r accumulators sit in order r; the fused layout's block g holds r = ks - 1 - g
             const int r = a.fused_r ? a.ks - 1 - blk : blk;
@@ -207,6 +229,46 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+    if (a.ws_partials == nullptr) return;
+    // ---- deterministic split-K, part 2: grid barrier (the launch is one co-resident wave), then every CTA folds its
+    // slice of dW over all splits, in split order, and adds it to the gradient: one plain read-modify-write per element
+    const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(a.ws_counters, 1u);
+        unsigned seen;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.ws_counters) : "memory"); } while (seen < n_ctas);
+    }
+    __syncthreads();
+    {
+        const int rows = a.ks * a.n_chunk;
+        const unsigned blk_elems = (unsigned)(a.ks * rows * n_co);
+        const unsigned total = blk_elems * (unsigned)a.groups;
+        const unsigned nsplit = gridDim.x, mtiles = gridDim.z;
+        for (unsigned e = cta * THREADS + threadIdx.x; e < total; e += n_ctas * THREADS) {
+            const unsigned g = e / blk_elems, within = e - g * blk_elems;
+            const unsigned co = within % (unsigned)n_co, t2 = within / (unsigned)n_co;
+            const unsigned rw = t2 % (unsigned)rows, blk = t2 / (unsigned)rows;
+            const float* src = a.ws_partials + (size_t)g * blk_elems + within;
+            float sum = 0.f;
+            for (unsigned sp = 0; sp < nsplit; ++sp) sum += __ldcg(src + (size_t)sp * a.groups * blk_elems);
+            const unsigned gnc = g / mtiles, gmt = g - gnc * mtiles;
+            const unsigned co_g = gmt * 128 + co;
+            if (co_g < (unsigned)a.cout) {
+                const int r = a.fused_r ? a.ks - 1 - (int)blk : (int)blk;
+                const int cig = a.ci_offset + (int)gnc * a.n_chunk + (int)(rw % (unsigned)a.n_chunk), st = (int)(rw / (unsigned)a.n_chunk);
+                a.dw[(((size_t)co_g * a.cin_total + cig) * a.ks + r) * a.ks + st] += sum;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(a.ws_counters + 1, 1u) == n_ctas - 1) {      // last CTA out: leave the counters ready for the next launch
+            a.ws_counters[0] = 0; a.ws_counters[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace wgrad
@@ -243,18 +305,23 @@ int encode(CUtensorMap* map, const void* ptr, int B, int H, int W, int Cs, int b
 }
 }  // namespace
 
-// dy: [B,H,W,dy_c_stride] bf16 (channels >= cout must be zero or absent), x: [B,H,W,x_c_stride] bf16 holding `cin`
-// channels of one K segment; dw: fp32 [cout][cin_total][ks][ks], ACCUMULATED into (caller zeroes it), the
-// segment's channels start at ci_offset.
-UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int x_c_stride, float* dw, int B, int H, int W,
-                             int cout, int cin, int cin_total, int ci_offset, int ks, cudaStream_t stream) {
-    if (dy == nullptr || x == nullptr || dw == nullptr || B <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
+namespace {
+struct WPlan {
+    WgradArgs a;
+    int splits, n_chunks, m_tiles, dy_rows, x_rows;
+    size_t smem, ws_bytes;
+};
+
+// Everything uaps_conv_wgrad decides before the launch.  ws_mode: deterministic split-K through a workspace (the splits'
+// partial sums cost two streaming passes over cout * cin * taps floats instead of that many fp32 atomics each, and the
+// launch must be ONE co-resident wave because the CTAs meet at a grid barrier).
+int plan_wgrad(int B, int H, int W, int cout, int cin, int cin_total, int ci_offset, int ks, bool ws_mode, WPlan* pl) {
+    if (B <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
     if (cout <= 0 || cin <= 0 || (ks != 1 && ks != 3) || ci_offset < 0 || ci_offset + cin > cin_total) return UAPS_EINVAL;
-    if ((dy_c_stride % 8) != 0 || (x_c_stride % 8) != 0 || dy_c_stride < cout || x_c_stride < cin) return UAPS_ERANGE;
-    if (!aligned_to(dy, 16) || !aligned_to(x, 16) || !aligned_to(dw, 4)) return UAPS_EALIGN;
     const int cin_pad = (cin + 15) / 16 * 16;
-    if (x_c_stride < cin_pad && (cin % 16) != 0) return UAPS_ERANGE;        // padded chunk must exist (zeros) in memory
-    WgradArgs a{};
+    if (cin_pad != cin) return UAPS_ERANGE;                                  // callers pad Cin=3 layers on their side (see conv.py)
+    WgradArgs& a = pl->a;
+    a = WgradArgs{};
     a.B = B; a.H = H; a.W = W; a.cout = cout; a.cin_total = cin_total; a.ci_offset = ci_offset; a.ks = ks;
     a.n_chunk = (cin_pad % 32 == 0) ? 32 : 16;
     a.tiles_x = (W + TILE_W - 1) / TILE_W; a.tiles_y = (H + TILE_H - 1) / TILE_H;
@@ -264,17 +331,15 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     a.a_ch = cout_pad >= 64 ? 64 : (cout_pad % 32 == 0 ? 32 : 16);
     a.n_co = cout_pad >= 128 ? 128 : cout_pad;
     if (a.n_co != 16 && a.n_co != 32 && a.n_co != 64 && a.n_co != 128) return UAPS_ERANGE;   // 48/80/96/112: not a UNet_UAPS shape
-    if (dy_c_stride < a.a_ch) return UAPS_ERANGE;                            // the dY box must lie inside the tensor's channels
-    a.dw = dw;
     static const bool no_m64 = getenv("UAPS_WGRAD_M128") != nullptr;           // A/B knob
     a.m_rows = (ks * a.n_chunk <= 64 && !no_m64) ? 64 : 128;
     static const bool no_fused = getenv("UAPS_WGRAD_PER_R") != nullptr;          // A/B knob
     a.fused_r = (ks == 3 && !a.two_boxes && a.n_co == a.a_ch && !no_fused) ? 1 : 0;
-    if (cin_pad != cin) return UAPS_ERANGE;                                  // callers pad Cin=3 layers on their side (see conv.py)
-    const int n_chunks = cin_pad / a.n_chunk, m_tiles = (cout + 127) / 128;
+    pl->n_chunks = cin_pad / a.n_chunk; pl->m_tiles = (cout + 127) / 128;
+    a.groups = pl->n_chunks * pl->m_tiles;
     const int row_a = a.a_ch * 2, row_b = a.n_chunk * 2;
-    const int dy_rows = TILE_H + (a.fused_r ? ks - 1 : 0), x_rows = TILE_H + (a.fused_r ? 0 : ks - 1);
-    const int a_bytes = (a.two_boxes ? 2 : 1) * dy_rows * TILE_W * row_a, b_bytes = x_rows * (TILE_W + ks - 1) * row_b;
+    pl->dy_rows = TILE_H + (a.fused_r ? ks - 1 : 0); pl->x_rows = TILE_H + (a.fused_r ? 0 : ks - 1);
+    const int a_bytes = (a.two_boxes ? 2 : 1) * pl->dy_rows * TILE_W * row_a, b_bytes = pl->x_rows * (TILE_W + ks - 1) * row_b;
     // ring depth: small-channel tiles are ~10 KB, so a deeper ring is cheap and hides the TMA latency better (measured)
     static const int stages_env = [] { const char* e = getenv("UAPS_WGRAD_STAGES"); return e ? atoi(e) : 0; }();
     const int stage_sz = (a_bytes + b_bytes + 1023) & ~1023;
@@ -283,42 +348,96 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     const int auto_stages = ks == 3 && stage_sz <= 12 * 1024 ? 8 : (ks == 3 && stage_sz <= 24 * 1024 ? 6 : 3);
     a.stages = stages_env >= 2 && stages_env <= MAX_STAGES ? stages_env : auto_stages;
     while (a.stages > 2 && (size_t)a.stages * stage_sz > 200 * 1024) --a.stages;
-    const size_t smem = (size_t)a.stages * stage_sz + 1024;
+    pl->smem = (size_t)a.stages * stage_sz + 1024;
     // split-K: enough CTAs to fill the machine (as many as fit per SM by shared memory and the 512 TMEM columns),
     // but at least 4 pixel tiles per CTA so the 9 * n_chunk * Cout reductions of the epilogue stay amortised
     int tmem_cols = 32;
     while (tmem_cols < ks * a.n_co) tmem_cols <<= 1;
-    int per_sm = (int)((227 * 1024) / (smem + 2048));
+    int per_sm = (int)((227 * 1024) / (pl->smem + 2048));
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
     static const int cap_env = [] { const char* e = getenv("UAPS_WGRAD_CTAS_PER_SM"); return e ? atoi(e) : 4; }();   // 6 measured slower
     if (per_sm > cap_env) per_sm = cap_env;
     if (per_sm < 1) per_sm = 1;
-    // split-K factor: trade main-loop length against the fp32 reductions of the epilogue (every split adds
-    // cout * cin * taps of them; measured ~125 reductions/ns chip-wide) -- evaluate a simple cost model
+    // split-K factor: trade main-loop length against the reduction of the splits' partial sums.  Atomic mode: every split
+    // adds cout * cin * taps fp32 atomics (measured ~125 reductions/ns chip-wide).  Workspace mode: every split adds one
+    // streaming write and one streaming read of that many floats (L2-resident, ~4 TB/s), plus a fixed grid-barrier cost.
     const int slots = per_sm * device_info().sm_count;
-    const int groups = n_chunks * m_tiles;
     const double tile_us = (12.0 * a.n_co + 300.0) / 1900.0;                 // tensor time 12 * Cout cycles per pixel tile + issue
-    const double red_per_split_us = (double)cout * cin * ks * ks / 125e3;
+    const double elems = (double)cout * cin * ks * ks;
+    const double red_per_split_us = ws_mode ? elems * 8.0 / 4.0e6 : elems / 125e3;
+    const int max_ctas = ws_mode ? slots : 4 * slots;
     int best = 1;
     double best_t = 1e30;
-    for (int sp = 1; sp <= a.tiles_total && sp * groups <= 4 * slots; sp = sp < 8 ? sp + 1 : sp + sp / 4) {
+    for (int sp = 1; sp <= a.tiles_total && sp * a.groups <= max_ctas; sp = sp < 8 ? sp + 1 : sp + sp / 4) {
         const int per_cta = (a.tiles_total + sp - 1) / sp;
-        const int waves = (sp * groups + slots - 1) / slots;
-        const double t = waves * per_cta * tile_us + sp * red_per_split_us + 3.0;
+        const int waves = (sp * a.groups + slots - 1) / slots;
+        const double t = waves * per_cta * tile_us + sp * red_per_split_us + (ws_mode ? 6.0 : 3.0);
         if (t < best_t) { best_t = t; best = sp; }
     }
-    int splits = best;
-    a.tiles_per_cta = (a.tiles_total + splits - 1) / splits;
-    splits = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    // the largest single-wave split count is always a candidate in workspace mode (the geometric search may step over it)
+    if (ws_mode && slots / a.groups >= 1) {
+        const int sp = slots / a.groups < a.tiles_total ? slots / a.groups : a.tiles_total;
+        const double t = ((a.tiles_total + sp - 1) / sp) * tile_us + sp * red_per_split_us + 6.0;
+        if (t < best_t) { best_t = t; best = sp; }
+    }
+    a.tiles_per_cta = (a.tiles_total + best - 1) / best;
+    pl->splits = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    pl->ws_bytes = WS_HEADER + (size_t)pl->splits * a.groups * ks * (ks * a.n_chunk) * a.n_co * sizeof(float);
+    return UAPS_OK;
+}
+}  // namespace
+
+// Bytes of workspace that make uaps_conv_wgrad take the deterministic split-K path for this shape (0: unsupported shape).
+UAPS_API size_t uaps_conv_wgrad_workspace_bytes(int B, int H, int W, int cout, int cin, int ks) {
+    WPlan pl;
+    if (plan_wgrad(B, H, W, cout, cin, cin, 0, ks, true, &pl) != UAPS_OK) return 0;
+    return pl.ws_bytes;
+}
+
+// dy: [B,H,W,dy_c_stride] bf16 (channels >= cout must be zero or absent), x: [B,H,W,x_c_stride] bf16 holding `cin`
+// channels of one K segment; dw: fp32 [cout][cin_total][ks][ks], ACCUMULATED into (caller zeroes it), the
+// segment's channels start at ci_offset.  workspace (nullable): >= uaps_conv_wgrad_workspace_bytes, 16-byte aligned, its
+// first 256 bytes zero before the first use (every launch leaves them zero): deterministic split-K without atomics.
+UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int x_c_stride, float* dw, int B, int H, int W,
+                             int cout, int cin, int cin_total, int ci_offset, int ks, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream) {
+    if (dy == nullptr || x == nullptr || dw == nullptr) return UAPS_EINVAL;
+    if ((dy_c_stride % 8) != 0 || (x_c_stride % 8) != 0 || dy_c_stride < cout || x_c_stride < cin) return UAPS_ERANGE;
+    if (!aligned_to(dy, 16) || !aligned_to(x, 16) || !aligned_to(dw, 4) || (workspace != nullptr && !aligned_to(workspace, 16)))
+        return UAPS_EALIGN;
+    static const bool no_ws = getenv("UAPS_WGRAD_ATOMIC") != nullptr;            // A/B knob: always the atomic epilogue
+    WPlan pl;
+    bool ws_mode = workspace != nullptr && !no_ws;
+    int rc = plan_wgrad(B, H, W, cout, cin, cin_total, ci_offset, ks, ws_mode, &pl);
+    if (rc != UAPS_OK) return rc;
+    if (ws_mode && pl.ws_bytes > workspace_bytes) {                              // too small: the atomic path still works
+        ws_mode = false;
+        rc = plan_wgrad(B, H, W, cout, cin, cin_total, ci_offset, ks, false, &pl);
+        if (rc != UAPS_OK) return rc;
+    }
+    WgradArgs& a = pl.a;
+    if (dy_c_stride < a.a_ch) return UAPS_ERANGE;                            // the dY box must lie inside the tensor's channels
+    a.dw = dw;
+    if (ws_mode) {
+        a.ws_counters = reinterpret_cast<unsigned*>(workspace);
+        a.ws_partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + WS_HEADER);
+    }
     CUtensorMap mdy, mx;
-    int rc = encode(&mdy, dy, B, H, W, dy_c_stride, a.a_ch, dy_rows, TILE_W);
+    rc = encode(&mdy, dy, B, H, W, dy_c_stride, a.a_ch, pl.dy_rows, TILE_W);
     if (rc != UAPS_OK) return rc;
-    rc = encode(&mx, x, B, H, W, x_c_stride, a.n_chunk, x_rows, TILE_W + ks - 1);
+    rc = encode(&mx, x, B, H, W, x_c_stride, a.n_chunk, pl.x_rows, TILE_W + ks - 1);
     if (rc != UAPS_OK) return rc;
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((unsigned)splits, (unsigned)n_chunks, (unsigned)m_tiles);
-    conv_wgrad_kernel<<<grid, THREADS, smem, stream>>>(mdy, mx, a);
+    if (ws_mode) {
+        // the grid barrier needs every CTA resident at once: check against what the hardware will really co-schedule
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_wgrad_kernel, THREADS, pl.smem) != cudaSuccess ||
+            (long long)occ * device_info().sm_count < (long long)pl.splits * a.groups)
+            return UAPS_ERANGE;
+    }
+    dim3 grid((unsigned)pl.splits, (unsigned)pl.n_chunks, (unsigned)pl.m_tiles);
+    conv_wgrad_kernel<<<grid, THREADS, pl.smem, stream>>>(mdy, mx, a);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }

@@ -15,11 +15,23 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Blocking wait: try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires, so a
+// waiting warp does not burn issue slots.  Without the hint the default suspend window is short and the retry loop
+// (BRA + SYNCS + YIELD) was 40 % of all instructions the 16-channel conv kernel executed (profiles/r01_conv_final16.txt),
+// competing with the epilogue warps of the 6 co-resident CTAs.  UAPS_MBAR_HINT_NS = 0 compiles the plain retry loop (A/B).
+#ifndef UAPS_MBAR_HINT_NS
+#define UAPS_MBAR_HINT_NS 0        // measured on B200 (profiles/r02_conv_layers_hint.txt): 20 us hint = no change on any layer
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
     while (!ok) {
+#if UAPS_MBAR_HINT_NS > 0
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)UAPS_MBAR_HINT_NS) : "memory");
+#else
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
