@@ -244,21 +244,42 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     {
         const int rows = a.ks * a.n_chunk;
         const unsigned blk_elems = (unsigned)(a.ks * rows * n_co);
-        const unsigned total = blk_elems * (unsigned)a.groups;
+        const unsigned total4 = blk_elems * (unsigned)a.groups / 4;        // n_co is a multiple of 16: groups of 4 output channels
         const unsigned nsplit = gridDim.x, mtiles = gridDim.z;
-        for (unsigned e = cta * THREADS + threadIdx.x; e < total; e += n_ctas * THREADS) {
+        const size_t split_stride = (size_t)a.groups * blk_elems;
+        for (unsigned e4 = cta * THREADS + threadIdx.x; e4 < total4; e4 += n_ctas * THREADS) {
+            const unsigned e = e4 * 4;
             const unsigned g = e / blk_elems, within = e - g * blk_elems;
             const unsigned co = within % (unsigned)n_co, t2 = within / (unsigned)n_co;
             const unsigned rw = t2 % (unsigned)rows, blk = t2 / (unsigned)rows;
-            const float* src = a.ws_partials + (size_t)g * blk_elems + within;
-            float sum = 0.f;
-            for (unsigned sp = 0; sp < nsplit; ++sp) sum += __ldcg(src + (size_t)sp * a.groups * blk_elems);
+            const float4* src = reinterpret_cast<const float4*>(a.ws_partials + (size_t)g * blk_elems + within);
+            // split order is fixed (deterministic); four independent partial sums keep four 16-byte loads in flight
+            float4 acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned sp = 0;
+            for (; sp + 4 <= nsplit; sp += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldcg(src + (size_t)(sp + u) * split_stride / 4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+            }
+            for (; sp < nsplit; ++sp) {
+                const float4 v = __ldcg(src + (size_t)sp * split_stride / 4);
+                acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+            }
+            const float sum[4] = {(acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                                  (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w)};
             const unsigned gnc = g / mtiles, gmt = g - gnc * mtiles;
-            const unsigned co_g = gmt * 128 + co;
-            if (co_g < (unsigned)a.cout) {
-                const int r = a.fused_r ? a.ks - 1 - (int)blk : (int)blk;
-                const int cig = a.ci_offset + (int)gnc * a.n_chunk + (int)(rw % (unsigned)a.n_chunk), st = (int)(rw / (unsigned)a.n_chunk);
-                a.dw[(((size_t)co_g * a.cin_total + cig) * a.ks + r) * a.ks + st] += sum;
+            const int r = a.fused_r ? a.ks - 1 - (int)blk : (int)blk;
+            const int cig = a.ci_offset + (int)gnc * a.n_chunk + (int)(rw % (unsigned)a.n_chunk), st = (int)(rw / (unsigned)a.n_chunk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned co_g = gmt * 128 + co + q;
+                // one writer per element and launch, so the result is still deterministic; a reduction (RED, no return value)
+                // instead of load-add-store keeps the scattered updates off the thread's critical path
+                if (co_g < (unsigned)a.cout) atomicAdd(a.dw + (((size_t)co_g * a.cin_total + cig) * a.ks + r) * a.ks + st, sum[q]);
             }
         }
     }
@@ -315,7 +336,8 @@ struct WPlan {
 // Everything uaps_conv_wgrad decides before the launch.  ws_mode: deterministic split-K through a workspace (the splits'
 // partial sums cost two streaming passes over cout * cin * taps floats instead of that many fp32 atomics each, and the
 // launch must be ONE co-resident wave because the CTAs meet at a grid barrier).
-int plan_wgrad(int B, int H, int W, int cout, int cin, int cin_total, int ci_offset, int ks, bool ws_mode, WPlan* pl) {
+int plan_wgrad(int B, int H, int W, int cout, int cin, int cin_total, int ci_offset, int ks, bool ws_mode, WPlan* pl,
+               int occ_cap = 0) {
     if (B <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
     if (cout <= 0 || cin <= 0 || (ks != 1 && ks != 3) || ci_offset < 0 || ci_offset + cin > cin_total) return UAPS_EINVAL;
     const int cin_pad = (cin + 15) / 16 * 16;
@@ -357,6 +379,7 @@ int plan_wgrad(int B, int H, int W, int cout, int cin, int cin_total, int ci_off
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
     static const int cap_env = [] { const char* e = getenv("UAPS_WGRAD_CTAS_PER_SM"); return e ? atoi(e) : 4; }();   // 6 measured slower
     if (per_sm > cap_env) per_sm = cap_env;
+    if (occ_cap > 0 && per_sm > occ_cap) per_sm = occ_cap;   // what the occupancy calculator says can really be co-resident
     if (per_sm < 1) per_sm = 1;
     // split-K factor: trade main-loop length against the reduction of the splits' partial sums.  Atomic mode: every split
     // adds cout * cin * taps fp32 atomics (measured ~125 reductions/ns chip-wide).  Workspace mode: every split adds one
@@ -391,7 +414,7 @@ int plan_wgrad(int B, int H, int W, int cout, int cin, int cin_total, int ci_off
 UAPS_API size_t uaps_conv_wgrad_workspace_bytes(int B, int H, int W, int cout, int cin, int ks) {
     WPlan pl;
     if (plan_wgrad(B, H, W, cout, cin, cin, 0, ks, true, &pl) != UAPS_OK) return 0;
-    return pl.ws_bytes;
+    return pl.ws_bytes;           // an upper bound: the launch may plan fewer splits once it knows the real occupancy
 }
 
 // dy: [B,H,W,dy_c_stride] bf16 (channels >= cout must be zero or absent), x: [B,H,W,x_c_stride] bf16 holding `cin`
@@ -407,9 +430,20 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
         return UAPS_EALIGN;
     static const bool no_ws = getenv("UAPS_WGRAD_ATOMIC") != nullptr;            // A/B knob: always the atomic epilogue
     WPlan pl;
-    bool ws_mode = workspace != nullptr && !no_ws;
+    // Few weights (16/32-channel and most 1x1 layers): the atomics cost a few microseconds while the fold of hundreds of
+    // splits would serialise -- those layers keep the atomic epilogue (measured: 85 us atomic vs 132 us folded, 16->16 @256x256).
+    static const long long ws_min = [] { const char* e = getenv("UAPS_WGRAD_WS_MIN_WEIGHTS"); return e ? atoll(e) : 16384ll; }();
+    bool ws_mode = workspace != nullptr && !no_ws && (long long)cout * cin * ks * ks >= ws_min;
     int rc = plan_wgrad(B, H, W, cout, cin, cin_total, ci_offset, ks, ws_mode, &pl);
     if (rc != UAPS_OK) return rc;
+    if (ws_mode) {                  // re-plan against the co-residency the occupancy calculator reports for this smem size
+        int occ = 0;
+        cudaError_t eo = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (eo == cudaSuccess) eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_wgrad_kernel, THREADS, pl.smem);
+        if (eo != cudaSuccess || occ < 1) { (void)cudaGetLastError(); ws_mode = false; }
+        rc = plan_wgrad(B, H, W, cout, cin, cin_total, ci_offset, ks, ws_mode, &pl, ws_mode ? occ : 0);
+        if (rc != UAPS_OK) return rc;
+    }
     if (ws_mode && pl.ws_bytes > workspace_bytes) {                              // too small: the atomic path still works
         ws_mode = false;
         rc = plan_wgrad(B, H, W, cout, cin, cin_total, ci_offset, ks, false, &pl);
@@ -429,15 +463,16 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     if (rc != UAPS_OK) return rc;
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return (int)e;
-    if (ws_mode) {
-        // the grid barrier needs every CTA resident at once: check against what the hardware will really co-schedule
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_wgrad_kernel, THREADS, pl.smem) != cudaSuccess ||
-            (long long)occ * device_info().sm_count < (long long)pl.splits * a.groups)
-            return UAPS_ERANGE;
-    }
     dim3 grid((unsigned)pl.splits, (unsigned)pl.n_chunks, (unsigned)pl.m_tiles);
-    conv_wgrad_kernel<<<grid, THREADS, pl.smem, stream>>>(mdy, mx, a);
+    if (ws_mode) {
+        // The grid barrier needs every CTA resident at once: it is launched as a COOPERATIVE kernel, which the driver
+        // refuses (instead of deadlocking) when the grid cannot be co-resident.
+        void* params[] = {(void*)&mdy, (void*)&mx, (void*)&a};
+        e = cudaLaunchCooperativeKernel((const void*)conv_wgrad_kernel, grid, dim3(THREADS), params, pl.smem, stream);
+        if (e != cudaSuccess) return (int)e;
+    } else {
+        conv_wgrad_kernel<<<grid, THREADS, pl.smem, stream>>>(mdy, mx, a);
+    }
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
