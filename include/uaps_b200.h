@@ -269,7 +269,8 @@ int uaps_nchw_f32_to_nhwc_bf16(const float* x, void* out, int B, int C, int H, i
  * _act normalises with the batch statistics, writes save_mean / save_rstd [C] and (if given) advances
  * running_mean / running_var with `momentum` (unbiased variance), as torch does.  The backward entry
  * recomputes the LeakyReLU sign and the Philox dropout mask from y and the seed; sum_g / sum_gx (fp64 [C],
- * zeroed by the caller) return d(beta) and d(gamma). */
+ * zeroed by the caller) return sum(g') = d(beta) and the RAW second moment sum(g' * y), from which
+ * d(gamma) = save_rstd * (sum_gx - save_mean * sum_g) (the dgamma_accum / dbeta_accum path applies that itself). */
 int uaps_bn_stats_nhwc(const void* y, int64_t npix, int C, double* sum, double* sumsq, cudaStream_t stream);
 int uaps_bn_act_nhwc(const void* y, const double* sum, const double* sumsq, const float* gamma,
                      const float* beta, float* running_mean, float* running_var, float momentum,

@@ -85,3 +85,20 @@ def test_metrics_match_reference_golden():
         acc = M.MetricAccumulator(dev)                    # per-batch means, as the reference's loop averages them
         acc.update(logits, mask)
         assert acc.result()["mDice"] == pytest.approx(float(c["mDice"]), rel=1e-9), name
+
+
+def test_out_of_range_labels_count_as_wrong_like_the_reference():
+    """utilities/metrics.py:8-13 divides the number of correct pixels by mask.numel(): a label outside [0, C) can never be
+    correct but stays in the denominator."""
+    from uaps_b200 import metrics as M
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(0)
+    logits = torch.randn(2, 4, 32, 32, generator=g, device=dev)
+    mask = torch.randint(0, 4, (2, 32, 32), generator=g, device=dev)
+    mask[0, :8] = 255                                       # an "ignore" region
+    pred = torch.argmax(torch.softmax(logits, 1), 1)
+    want = float(torch.eq(pred, mask).sum()) / float(mask.numel())
+    assert M.pixel_accuracy(logits, mask) == pytest.approx(want, rel=1e-12)
+    acc = M.MetricAccumulator(dev)
+    acc.update(logits, mask)
+    assert acc.result()["pixel_accuracy"] == pytest.approx(want, rel=1e-12)

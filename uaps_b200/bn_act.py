@@ -62,7 +62,10 @@ class _BnActFn(torch.autograd.Function):
                                                  B * H * W, C, seed_dev, L.stream_ptr()), "uaps_bn_act_bwd_nhwc")
         if direct:                               # already added into gamma.grad / beta.grad by the kernel
             return (dy,) + (None,) * 10
-        return (dy, sums[C:].float(), sums[:C].float()) + (None,) * 8
+        # the kernel accumulates sum(g') and the RAW sum(g' * y); d gamma = sum(g' * xhat) = rstd * (sum(g' y) - mean * sum(g'))
+        sg, sgy = sums[:C], sums[C:]
+        dgamma = stats[C:].double() * (sgy - stats[:C].double() * sg)
+        return (dy, dgamma.float(), sg.float()) + (None,) * 8
 
 
 def bn_lrelu_dropout(y: torch.Tensor, bn: torch.nn.BatchNorm2d, p_drop: float = 0.0, slope: float = 0.01,

@@ -12,6 +12,7 @@
 // Layout: y is [npix, C] bf16, C a power of two in 8..256.  G = C/8 adjacent threads own the eight
 // 16-byte chunks of a pixel; a thread's channels are fixed over its grid-stride loop, so per-channel
 // sums are private registers until one shared-memory + one fp64 global atomic per channel per CTA.
+#include <cstdlib>
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -184,73 +185,88 @@ __global__ void __launch_bounds__(BT) bn_act_kernel(const uint4* __restrict__ y,
     });
 }
 
-// g' = g * dropout' * leaky_relu'(z); accumulate sum(g') and sum(g' * xhat) per channel
-__global__ void __launch_bounds__(BT) bn_act_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
-                                                               const BnParams p, double* __restrict__ sum_g,
-                                                               double* __restrict__ sum_gx) {
+// g' = g * dropout' * leaky_relu'(z); accumulate sum(g') and sum(g' * y) per channel.
+// The kernels are instruction-issue bound (ncu: 64 % issue-active at 23 % occupancy, profiles/r02_kernels_a.txt), so the
+// per-element work is folded into per-channel constants: z = y * sc + sh with sc = gamma * rstd, sh = beta - mean * sc
+// (one FMA instead of subtract / multiply / FMA), and the RAW second moment sum(g' * y) is accumulated -- the consumer
+// recovers sum(g' * xhat) = rstd * (sum(g' * y) - mean * sum(g')) in fp64.
+template <int U, int MINB>
+__global__ void __launch_bounds__(BT, MINB) bn_act_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                                                                  const BnParams p, double* __restrict__ sum_g,
+                                                                  double* __restrict__ sum_gy) {
     __shared__ float s_a[256], s_b[256];
     const int chunk = threadIdx.x % p.G;
     const uint64_t seed = p.p > 0.f ? eff_seed(p) : 0ull;
-    float mean[8], rstd[8], ga[8], be[8];
+    float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = chunk * 8 + i;
-        mean[i] = p.save_mean[c]; rstd[i] = p.save_rstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c];
+        sc[i] = p.gamma[c] * p.save_rstd[c];
+        sh[i] = p.beta[c] - p.save_mean[c] * sc[i];
     }
     float a[8], b[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
     const long long total = p.npix * p.G;
-    stream_chunks<4>(total, [&](long long t) { return Pair16{__ldg(g + t), __ldg(y + t)}; }, [&](long long t, const Pair16& pk) {
+    stream_chunks<U>(total, [&](long long t) { return Pair16{__ldg(g + t), __ldg(y + t)}; }, [&](long long t, const Pair16& pk) {
         float gv[8], v[8], k[8];
         unpack8(pk.g, gv);
         unpack8(pk.y, v);
         if (p.p > 0.f) keep8(seed, (uint64_t)t, p.p, k);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float xh = (v[i] - mean[i]) * rstd[i];
-            const float z = fmaf(ga[i], xh, be[i]);
+            const float z = fmaf(v[i], sc[i], sh[i]);
             float gp = gv[i] * (z > 0.f ? 1.f : p.slope);
             if (p.p > 0.f) gp *= k[i] * p.keep_scale;
             a[i] += gp;
-            b[i] = fmaf(gp, xh, b[i]);
+            b[i] = fmaf(gp, v[i], b[i]);
         }
     });
-    cta_accumulate<false>(a, b, p.G, s_a, s_b, sum_g, sum_gx);
+    cta_accumulate<false>(a, b, p.G, s_a, s_b, sum_g, sum_gy);
 }
 
-// dy = gamma * rstd * (g' - mean(g') - xhat * mean(g' * xhat))
-__global__ void __launch_bounds__(BT) bn_act_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
-                                                        uint4* __restrict__ dy, const BnParams p) {
-    if (blockIdx.x == 0 && p.dgamma_accum != nullptr) {       // d gamma = sum(g' * xhat), d beta = sum(g'): add to .grad
-        for (int c = threadIdx.x; c < 8 * p.G; c += BT) {
-            p.dgamma_accum[c] += (float)p.sumsq[c];
-            p.dbeta_accum[c] += (float)p.sum[c];
+// dy = gamma * rstd * (g' - mean(g') - xhat * mean(g' * xhat)) = g' * A + y * Bc + Cc with per-channel
+//   A = gamma * rstd, Bc = -A * rstd * mgx, Cc = A * (mean * rstd * mgx - mg),  mg = sum(g') / n,  mgx = sum(g' * xhat) / n
+template <int U, int MINB>
+__global__ void __launch_bounds__(BT, MINB) bn_act_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                                                           uint4* __restrict__ dy, const BnParams p) {
+    __shared__ float s_A[256], s_sh[256], s_B[256], s_C[256];
+    const int C = 8 * p.G;
+    const double invn = 1.0 / (double)p.npix;
+    for (int c = threadIdx.x; c < C; c += BT) {
+        const double mean = (double)p.save_mean[c], rstd = (double)p.save_rstd[c], ga = (double)p.gamma[c];
+        const double sg = p.sum[c], sgx = rstd * (p.sumsq[c] - mean * sg);      // sum(g'), sum(g' * xhat)
+        const double A = ga * rstd, mg = sg * invn, mgx = sgx * invn;
+        s_A[c] = (float)A;
+        s_sh[c] = (float)((double)p.beta[c] - mean * A);
+        s_B[c] = (float)(-A * rstd * mgx);
+        s_C[c] = (float)(A * (mean * rstd * mgx - mg));
+        if (blockIdx.x == 0 && p.dgamma_accum != nullptr) {   // d gamma = sum(g' * xhat), d beta = sum(g'): add to .grad
+            p.dgamma_accum[c] += (float)sgx;
+            p.dbeta_accum[c] += (float)sg;
         }
     }
+    __syncthreads();
     const int chunk = threadIdx.x % p.G;
     const uint64_t seed = p.p > 0.f ? eff_seed(p) : 0ull;
-    const float invn = (float)(1.0 / (double)p.npix);
-    float mean[8], rstd[8], ga[8], be[8], mg[8], mgx[8];
+    float A[8], sh[8], Bc[8], Cc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = chunk * 8 + i;
-        mean[i] = p.save_mean[c]; rstd[i] = p.save_rstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c];
-        mg[i] = (float)p.sum[c] * invn; mgx[i] = (float)p.sumsq[c] * invn;
+        A[i] = s_A[c]; sh[i] = s_sh[c]; Bc[i] = s_B[c]; Cc[i] = s_C[c];
     }
     const long long total = p.npix * p.G;
-    stream_chunks<2>(total, [&](long long t) { return Pair16{__ldg(g + t), __ldg(y + t)}; }, [&](long long t, const Pair16& pk) {
+    stream_chunks<U>(total, [&](long long t) { return Pair16{__ldg(g + t), __ldg(y + t)}; }, [&](long long t, const Pair16& pk) {
         float gv[8], v[8], k[8];
         unpack8(pk.g, gv);
         unpack8(pk.y, v);
         if (p.p > 0.f) keep8(seed, (uint64_t)t, p.p, k);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float xh = (v[i] - mean[i]) * rstd[i];
-            const float z = fmaf(ga[i], xh, be[i]);
+            const float z = fmaf(v[i], A[i], sh[i]);
             float gp = gv[i] * (z > 0.f ? 1.f : p.slope);
             if (p.p > 0.f) gp *= k[i] * p.keep_scale;
-            v[i] = ga[i] * rstd[i] * (gp - mg[i] - xh * mgx[i]);
+            v[i] = fmaf(gp, A[i], fmaf(v[i], Bc[i], Cc[i]));
         }
         dy[t] = pack8(v);
     });
@@ -315,13 +331,22 @@ UAPS_API int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float*
     p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
     if ((dgamma_accum == nullptr) != (dbeta_accum == nullptr)) return UAPS_EINVAL;
     p.dgamma_accum = dgamma_accum; p.dbeta_accum = dbeta_accum; p.seed_dev = seed_dev;
-    const int grid = bn_grid(npix * (C / 8), 2);       // ~124 registers: 2 resident CTAs/SM = one persistent wave
-    // sum_g / sum_gx (zeroed by the caller) receive sum(g') and sum(g' * xhat) = d beta and d gamma
-    bn_act_bwd_reduce_kernel<<<bn_grid(npix * (C / 8), 2), BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y), p,
-                                                     sum_g, sum_gx);
-    UAPS_LAUNCH_CHECK();
-    bn_act_bwd_kernel<<<grid, BT, 0, stream>>>(reinterpret_cast<const uint4*>(g_out), reinterpret_cast<const uint4*>(y),
-                                              reinterpret_cast<uint4*>(dy), p);
+    // sum_g / sum_gx (zeroed by the caller) receive sum(g') and the RAW sum(g' * y); the second kernel turns the latter into
+    // sum(g' * xhat) = d gamma.  Variant = (loads in flight per thread, resident CTAs / SM); UAPS_BN_BWD_VARIANT picks (A/B knob).
+    static const int variant = [] { const char* e = getenv("UAPS_BN_BWD_VARIANT"); return e ? atoi(e) : 1; }();
+    const uint4* g4 = reinterpret_cast<const uint4*>(g_out);
+    const uint4* y4 = reinterpret_cast<const uint4*>(y);
+    uint4* dy4 = reinterpret_cast<uint4*>(dy);
+    const long long chunks = npix * (C / 8);
+#define UAPS_BN_BWD(U1, M1, U2, M2)                                                                          \
+    bn_act_bwd_reduce_kernel<U1, M1><<<bn_grid(chunks, M1), BT, 0, stream>>>(g4, y4, p, sum_g, sum_gx);      \
+    UAPS_LAUNCH_CHECK();                                                                                     \
+    bn_act_bwd_kernel<U2, M2><<<bn_grid(chunks, M2), BT, 0, stream>>>(g4, y4, dy4, p);
+    if (variant == 0) { UAPS_BN_BWD(4, 2, 2, 2) }
+    else if (variant == 1) { UAPS_BN_BWD(3, 3, 2, 3) }
+    else if (variant == 3) { UAPS_BN_BWD(2, 4, 2, 4) }
+    else { UAPS_BN_BWD(2, 3, 2, 3) }
+#undef UAPS_BN_BWD
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }

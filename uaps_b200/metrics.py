@@ -26,11 +26,13 @@ def confusion(logits: torch.Tensor, mask: torch.Tensor, out: torch.Tensor = None
     return conf
 
 
-def metrics_from_confusion(conf: torch.Tensor, smooth: float = 1e-10):
+def metrics_from_confusion(conf: torch.Tensor, smooth: float = 1e-10, n_pixels: int = None):
     """(pixel_accuracy, mIoU, mDice) as 0-dim device tensors, the reference's formulas: classes 1..C-1, classes
-    absent from the labels skipped (np.nanmean), smooth 1e-10."""
+    absent from the labels skipped (np.nanmean), smooth 1e-10.  n_pixels: the accuracy's denominator -- the reference
+    divides by ``mask.numel()`` (utilities/metrics.py:12), so a pixel whose label lies outside [0, C) (an ignore
+    index) counts as WRONG there; the confusion matrix does not hold such pixels, hence the explicit total."""
     c = conf.double()
-    acc = c.diagonal().sum() / c.sum()
+    acc = c.diagonal().sum() / (c.sum() if n_pixels is None else float(n_pixels))
     inter = c.diagonal()[1:]
     label_n, pred_n = c.sum(1)[1:], c.sum(0)[1:]
     union = label_n + pred_n - inter
@@ -45,7 +47,7 @@ def metrics_from_confusion(conf: torch.Tensor, smooth: float = 1e-10):
 
 
 def pixel_accuracy(output: torch.Tensor, mask: torch.Tensor) -> float:
-    return float(metrics_from_confusion(confusion(output, mask))[0])
+    return float(metrics_from_confusion(confusion(output, mask), n_pixels=mask.numel())[0])
 
 
 def mIoU(pred_mask: torch.Tensor, mask: torch.Tensor, smooth: float = 1e-10, n_classes: int = 4) -> float:
@@ -65,7 +67,7 @@ class MetricAccumulator:
         self.batches = 0
 
     def update(self, logits: torch.Tensor, mask: torch.Tensor) -> None:
-        self.sums += torch.stack(metrics_from_confusion(confusion(logits, mask)))
+        self.sums += torch.stack(metrics_from_confusion(confusion(logits, mask), n_pixels=mask.numel()))
         self.batches += 1
 
     def result(self):
