@@ -114,6 +114,8 @@ struct Pair16 { uint4 g, y; };
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(BT) bn_stats_kernel(const uint4* __restrict__ y, long long npix, int G,
                                                       double* __restrict__ sum, double* __restrict__ sumsq) {
     __shared__ float s_a[256], s_b[256];
+    grid_dep_launch();
+    grid_dep_wait();
     const long long total = npix * G;
     float a[8], b[8];
 #pragma unroll
@@ -144,6 +146,8 @@ __device__ __forceinline__ uint64_t eff_seed(const BnParams& p) { return p.seed 
 // forward: a = dropout(leaky_relu(gamma * (y - mean) * rstd + beta))
 __global__ void __launch_bounds__(BT) bn_act_kernel(const uint4* __restrict__ y, uint4* __restrict__ out, const BnParams p) {
     __shared__ float s_scale[256], s_shift[256];
+    grid_dep_launch();
+    grid_dep_wait();
     const int C = 8 * p.G;
     const double n = (double)p.npix;
     for (int c = threadIdx.x; c < C; c += BT) {
@@ -195,6 +199,8 @@ __global__ void __launch_bounds__(BT, MINB) bn_act_bwd_reduce_kernel(const uint4
                                                                   const BnParams p, double* __restrict__ sum_g,
                                                                   double* __restrict__ sum_gy) {
     __shared__ float s_a[256], s_b[256];
+    grid_dep_launch();
+    grid_dep_wait();
     const int chunk = threadIdx.x % p.G;
     const uint64_t seed = p.p > 0.f ? eff_seed(p) : 0ull;
     float sc[8], sh[8];
@@ -231,6 +237,8 @@ template <int U, int MINB>
 __global__ void __launch_bounds__(BT, MINB) bn_act_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
                                                            uint4* __restrict__ dy, const BnParams p) {
     __shared__ float s_A[256], s_sh[256], s_B[256], s_C[256];
+    grid_dep_launch();
+    grid_dep_wait();
     const int C = 8 * p.G;
     const double invn = 1.0 / (double)p.npix;
     for (int c = threadIdx.x; c < C; c += BT) {
@@ -292,7 +300,8 @@ UAPS_API int uaps_bn_stats_nhwc(const void* y, int64_t npix, int C, double* sum,
     if (y == nullptr || sum == nullptr || sumsq == nullptr || npix <= 0) return UAPS_EINVAL;
     if (!valid_c(C)) return UAPS_ERANGE;
     if (!aligned_to(y, 16) || !aligned_to(sum, 8) || !aligned_to(sumsq, 8)) return UAPS_EALIGN;
-    bn_stats_kernel<<<bn_grid_clustered(npix * (C / 8), 4), BT, 0, stream>>>(reinterpret_cast<const uint4*>(y), npix, C / 8, sum, sumsq);
+    UAPS_LAUNCH(bn_stats_kernel, dim3(bn_grid_clustered(npix * (C / 8), 4)), dim3(BT), 0, stream, reinterpret_cast<const uint4*>(y),
+                (long long)npix, C / 8, sum, sumsq);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -311,7 +320,8 @@ UAPS_API int uaps_bn_act_nhwc(const void* y, const double* sum, const double* su
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.momentum = momentum; p.eps = eps; p.slope = slope; p.p = (float)p_drop;
     p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;
     p.seed_dev = seed_dev;
-    bn_act_kernel<<<bn_grid(npix * (C / 8), 4), BT, 0, stream>>>(reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(out), p);
+    UAPS_LAUNCH(bn_act_kernel, dim3(bn_grid(npix * (C / 8), 4)), dim3(BT), 0, stream, reinterpret_cast<const uint4*>(y),
+                reinterpret_cast<uint4*>(out), p);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -339,9 +349,9 @@ UAPS_API int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float*
     uint4* dy4 = reinterpret_cast<uint4*>(dy);
     const long long chunks = npix * (C / 8);
 #define UAPS_BN_BWD(U1, M1, U2, M2)                                                                          \
-    bn_act_bwd_reduce_kernel<U1, M1><<<bn_grid(chunks, M1), BT, 0, stream>>>(g4, y4, p, sum_g, sum_gx);      \
+    UAPS_LAUNCH((bn_act_bwd_reduce_kernel<U1, M1>), dim3(bn_grid(chunks, M1)), dim3(BT), 0, stream, g4, y4, p, sum_g, sum_gx); \
     UAPS_LAUNCH_CHECK();                                                                                     \
-    bn_act_bwd_kernel<U2, M2><<<bn_grid(chunks, M2), BT, 0, stream>>>(g4, y4, dy4, p);
+    UAPS_LAUNCH((bn_act_bwd_kernel<U2, M2>), dim3(bn_grid(chunks, M2)), dim3(BT), 0, stream, g4, y4, dy4, p);
     if (variant == 0) { UAPS_BN_BWD(4, 2, 2, 2) }
     else if (variant == 1) { UAPS_BN_BWD(3, 3, 2, 3) }
     else if (variant == 3) { UAPS_BN_BWD(2, 4, 2, 4) }

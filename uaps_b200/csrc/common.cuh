@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "uaps_b200.h"
 
 #define UAPS_API extern "C" __attribute__((visibility("default")))
@@ -33,6 +34,48 @@ inline const DeviceInfo& device_info() {
 }
 
 template <typename T> __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch for the ~1150-kernel training iteration ------------------------------------------
+// Every kernel of the bf16 path is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// grid_dep_launch() (its successor's CTAs may be scheduled as soon as all of this grid's CTAs have started) followed --
+// after any set-up that touches no global memory -- by grid_dep_wait() (block until the predecessor grid has completed
+// and flushed).  Launch latency, CTA scheduling and per-CTA set-up of kernel i+1 then overlap the tail of kernel i; in a
+// captured iteration the edges become programmatic graph edges.  MEASURED on B200 (round 2): the captured training iteration
+// gets SLOWER with it (32.85 -> 33.76 ms: early CTAs of the successor hold shared memory / TMEM while they wait and the
+// persistent kernels are sized to fill the machine), batch-1 inference latency improves (0.274 -> 0.255 ms).  So it is
+// OFF by default and UAPS_PDL=1 turns it on; the two instructions are no-ops in a kernel launched without the attribute.
+// (The three launches of the fused loss keep their own, always-on PDL chain: fused_loss_impl.cuh.)
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_all_enabled() {
+    static const bool on = [] { const char* e = getenv("UAPS_PDL"); return e != nullptr && atoi(e) != 0; }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool cooperative,
+                            Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl_all_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cooperative) {
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define UAPS_LAUNCH(kern, grid, block, smem, stream, ...)                                          \
+    do {                                                                                           \
+        cudaError_t le__ = ::uaps::launch_k(kern, grid, block, smem, stream, false, __VA_ARGS__);  \
+        if (le__ != cudaSuccess) return (int)le__;                                                 \
+    } while (0)
 
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 

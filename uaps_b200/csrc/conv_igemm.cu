@@ -94,6 +94,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], done_bar;
     __shared__ uint32_t tmem_base_smem;
+    grid_dep_launch();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = a.ks - 1;
@@ -123,6 +124,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
+    // everything above (barrier init, TMEM allocation) touched no global memory: it overlapped the predecessor's tail
+    grid_dep_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -235,6 +238,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2], w_bar;
     __shared__ uint32_t tmem_base_smem;
+    grid_dep_launch();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = a.ks - 1;
@@ -262,6 +266,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
+    // everything above (barrier init, TMEM allocation) touched no global memory: it overlapped the predecessor's tail
+    grid_dep_wait();
     const int spatial = a.tiles_x * a.tiles_y;
 
     if (warp == 0) {
@@ -470,6 +476,8 @@ __device__ __forceinline__ float logical_w(const PackArgs& p, int co, int ci, in
 // folded pixels; virtual weight [(b,co)][(a,ci)][r][dj] = W[co][ci][r][s] with s = (dj-1)*F + a - b + 1 when
 // that is a real tap, else 0.  F x more MACs (free: these layers are bandwidth bound), F x wider TMA rows.
 __global__ void pack_weights_kernel(PackArgs p) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int F = p.fold;
     const int chunks_per_row = p.ck / 8;
     const int chunks0 = F * p.seg_mem[0] / p.ck, chunks1 = p.nseg > 1 ? F * p.seg_mem[1] / p.ck : 0;
@@ -599,7 +607,7 @@ UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, in
     p.fold = fold; p.transpose = transpose;
     const long long total = (long long)pl.packed_bytes / 16;
     const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    pack_weights_kernel<<<grid, 256, 0, stream>>>(p);
+    UAPS_LAUNCH(pack_weights_kernel, dim3(grid), dim3(256), 0, stream, p);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -688,7 +696,7 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
 #define UAPS_CONV_LAUNCH(CKV)                                                                                   \
         e = cudaFuncSetAttribute(conv_igemm_kernel<CKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         if (e != cudaSuccess) return (int)e;                                                                        \
-        conv_igemm_kernel<CKV><<<grid, THREADS, smem, stream>>>(m0, m1, a);
+        UAPS_LAUNCH(conv_igemm_kernel<CKV>, grid, dim3(THREADS), smem, stream, m0, m1, a);
         if (pl.ck == 64) { UAPS_CONV_LAUNCH(64) } else if (pl.ck == 32) { UAPS_CONV_LAUNCH(32) } else { UAPS_CONV_LAUNCH(16) }
 #undef UAPS_CONV_LAUNCH
     } else {
@@ -716,7 +724,7 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
 #define UAPS_CONV_LAUNCH2(CKV)                                                                                             \
         e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<CKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         if (e != cudaSuccess) return (int)e;                                                                                   \
-        conv_igemm_persistent_kernel<CKV><<<(unsigned)gridx, THREADS2, smem, stream>>>(m0, m1, a);
+        UAPS_LAUNCH(conv_igemm_persistent_kernel<CKV>, dim3((unsigned)gridx), dim3(THREADS2), smem, stream, m0, m1, a);
         if (pl.ck == 64) { UAPS_CONV_LAUNCH2(64) } else if (pl.ck == 32) { UAPS_CONV_LAUNCH2(32) } else { UAPS_CONV_LAUNCH2(16) }
 #undef UAPS_CONV_LAUNCH2
     }

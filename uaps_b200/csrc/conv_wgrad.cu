@@ -71,6 +71,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], done_bar;
     const int STAGES = a.stages;
     __shared__ uint32_t tmem_base_smem;
+    grid_dep_launch();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = a.ks - 1;
@@ -108,6 +109,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
+    grid_dep_wait();                    // the set-up above touched no global memory: it overlapped the predecessor's tail
 
     if (ntiles > 0) {
         if (warp == 0) {
@@ -467,11 +469,10 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     if (ws_mode) {
         // The grid barrier needs every CTA resident at once: it is launched as a COOPERATIVE kernel, which the driver
         // refuses (instead of deadlocking) when the grid cannot be co-resident.
-        void* params[] = {(void*)&mdy, (void*)&mx, (void*)&a};
-        e = cudaLaunchCooperativeKernel((const void*)conv_wgrad_kernel, grid, dim3(THREADS), params, pl.smem, stream);
+        e = launch_k(conv_wgrad_kernel, grid, dim3(THREADS), pl.smem, stream, true, mdy, mx, a);
         if (e != cudaSuccess) return (int)e;
     } else {
-        conv_wgrad_kernel<<<grid, THREADS, pl.smem, stream>>>(mdy, mx, a);
+        UAPS_LAUNCH(conv_wgrad_kernel, grid, dim3(THREADS), pl.smem, stream, mdy, mx, a);
     }
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;

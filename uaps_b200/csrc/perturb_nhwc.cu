@@ -40,6 +40,8 @@ __device__ __forceinline__ void uniform8(uint64_t seed, uint64_t idx, uint32_t s
 // attention[b,p] = mean_c x[b,p,c]; smax[b] = max_p attention (order-preserving atomicMax)
 __global__ void __launch_bounds__(PT) fdrop_stats_nhwc_kernel(const uint4* __restrict__ x, int G, long long HW, int B,
                                                               float* __restrict__ attention, uint32_t* __restrict__ smax_enc) {
+    grid_dep_launch();
+    grid_dep_wait();
     const long long chunks_per_sample = HW * G;       // a multiple of 32 (checked by the caller): warps stay whole
     const float invC = 1.0f / (8 * G);
     __shared__ float s_m[PT / kWarp];
@@ -76,6 +78,8 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
                                                            float u, uint4* __restrict__ y_noise, uint4* __restrict__ y_drop,
                                                            uint4* __restrict__ y_fdrop, uint4* __restrict__ dx, int G, long long HW, int B,
                                                            const uint64_t* __restrict__ seed_dev, const float* __restrict__ u_dev) {
+    grid_dep_launch();
+    grid_dep_wait();
     if (seed_dev != nullptr) seed += *seed_dev;       // device-resident step state (uaps_step_begin)
     if (u_dev != nullptr) u = *u_dev;
     const long long chunks_per_sample = HW * G;
@@ -156,7 +160,7 @@ UAPS_API int uaps_fdrop_stats_nhwc(const void* x, int B, int C, int64_t HW, floa
     long long gx = ceil_div<long long>(HW * G, PT), cap = ceil_div<long long>((long long)device_info().sm_count * 8, B);
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)(gx < 1 ? 1 : gx), (unsigned)(B < 65535 ? B : 65535), 1);
-    fdrop_stats_nhwc_kernel<<<grid, PT, 0, stream>>>(reinterpret_cast<const uint4*>(x), G, HW, B, attention, smax_enc);
+    UAPS_LAUNCH(fdrop_stats_nhwc_kernel, grid, dim3(PT), 0, stream, reinterpret_cast<const uint4*>(x), G, (long long)HW, B, attention, smax_enc);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -170,10 +174,10 @@ UAPS_API int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range,
     if (!valid_g(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
     if (!aligned_to(x, 16) || !aligned_to(y_noise, 16) || !aligned_to(y_drop, 16) || !aligned_to(y_fdrop, 16)) return UAPS_EALIGN;
     const float pk = (float)(1.0 - p_drop);
-    perturb3_nhwc_kernel<false><<<grid1d(HW * (C / 8) * B), PT, 0, stream>>>(
-        reinterpret_cast<const uint4*>(x), nullptr, nullptr, nullptr, seed, noise_range, (float)p_drop, (float)(1.0 / (double)pk),
-        attention, smax_enc, u, reinterpret_cast<uint4*>(y_noise), reinterpret_cast<uint4*>(y_drop),
-        reinterpret_cast<uint4*>(y_fdrop), nullptr, C / 8, HW, B, seed_dev, u_dev);
+    UAPS_LAUNCH(perturb3_nhwc_kernel<false>, dim3(grid1d(HW * (C / 8) * B)), dim3(PT), 0, stream,
+        reinterpret_cast<const uint4*>(x), (const uint4*)nullptr, (const uint4*)nullptr, (const uint4*)nullptr, seed, noise_range,
+        (float)p_drop, (float)(1.0 / (double)pk), attention, smax_enc, u, reinterpret_cast<uint4*>(y_noise),
+        reinterpret_cast<uint4*>(y_drop), reinterpret_cast<uint4*>(y_fdrop), (uint4*)nullptr, C / 8, (long long)HW, B, seed_dev, u_dev);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -188,10 +192,10 @@ UAPS_API int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, con
     if (!valid_g(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
     if (!aligned_to(dx, 16) || !aligned_to(g_noise, 16) || !aligned_to(g_drop, 16) || !aligned_to(g_fdrop, 16)) return UAPS_EALIGN;
     const float pk = (float)(1.0 - p_drop);
-    perturb3_nhwc_kernel<true><<<grid1d(HW * (C / 8) * B), PT, 0, stream>>>(
-        nullptr, reinterpret_cast<const uint4*>(g_noise), reinterpret_cast<const uint4*>(g_drop),
+    UAPS_LAUNCH(perturb3_nhwc_kernel<true>, dim3(grid1d(HW * (C / 8) * B)), dim3(PT), 0, stream,
+        (const uint4*)nullptr, reinterpret_cast<const uint4*>(g_noise), reinterpret_cast<const uint4*>(g_drop),
         reinterpret_cast<const uint4*>(g_fdrop), seed, noise_range, (float)p_drop, (float)(1.0 / (double)pk), attention, smax_enc, u,
-        nullptr, nullptr, nullptr, reinterpret_cast<uint4*>(dx), C / 8, HW, B, seed_dev, u_dev);
+        (uint4*)nullptr, (uint4*)nullptr, (uint4*)nullptr, reinterpret_cast<uint4*>(dx), C / 8, (long long)HW, B, seed_dev, u_dev);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }

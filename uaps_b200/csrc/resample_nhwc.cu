@@ -40,6 +40,8 @@ constexpr int RX = 32, RY = 8;            // CTA = 32 chunks x 8 rows = 256 thre
 
 __global__ void __launch_bounds__(RT) upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W,
                                                             int G, float sh, float sw) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int OH = 2 * H, OW = 2 * W;
     const unsigned col = blockIdx.x * RX + threadIdx.x;
     const int oy = blockIdx.y * RY + threadIdx.y;
@@ -73,6 +75,8 @@ __device__ __forceinline__ float tap_weight(int o, int i, float scale, int in_si
 constexpr int NCAND = 6;
 __global__ void __launch_bounds__(RT) upsample2x_bwd_kernel(const uint4* __restrict__ gy, uint4* __restrict__ gx, int H, int W,
                                                             int G, float sh, float sw) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int OH = 2 * H, OW = 2 * W;
     const unsigned col = blockIdx.x * RX + threadIdx.x;
     const int iy = blockIdx.y * RY + threadIdx.y;
@@ -110,6 +114,8 @@ __global__ void __launch_bounds__(RT) upsample2x_bwd_kernel(const uint4* __restr
 // logits gradient entering the bf16 path.  One thread per pixel: per channel a warp reads 128 contiguous bytes.
 __global__ void __launch_bounds__(RT) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, uint4* __restrict__ out, int C,
                                                                    int HW, int Gp) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int p = blockIdx.x * RT + threadIdx.x;
     if (p >= HW) return;
     const float* xb = x + (size_t)blockIdx.y * C * HW + p;
@@ -126,6 +132,8 @@ __global__ void __launch_bounds__(RT) nchw_f32_to_nhwc_bf16_kernel(const float* 
 }
 
 __global__ void __launch_bounds__(RT) maxpool2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int G) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int OH = H / 2, OW = W / 2;
     const long long total = (long long)B * OH * OW * G;
     for (long long t = (long long)blockIdx.x * RT + threadIdx.x; t < total; t += (long long)gridDim.x * RT) {
@@ -147,6 +155,8 @@ __global__ void __launch_bounds__(RT) maxpool2_fwd_kernel(const uint4* __restric
 // the gradient goes to the first maximum of the window in (row, column) order, as torch's max_pool2d backward does
 __global__ void __launch_bounds__(RT) maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gy,
                                                           uint4* __restrict__ gx, int B, int H, int W, int G) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int OH = H / 2, OW = W / 2;
     const long long total = (long long)B * OH * OW * G;
     for (long long t = (long long)blockIdx.x * RT + threadIdx.x; t < total; t += (long long)gridDim.x * RT) {
@@ -195,11 +205,11 @@ UAPS_API int uaps_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, i
     if (B > 65535 || ceil_div(2 * H, RY) > 65535) return UAPS_ERANGE;
     const dim3 block(RX, RY);
     if (!backward)      // x: [B,H,W,C] -> y: [B,2H,2W,C]
-        upsample2x_fwd_kernel<<<dim3(ceil_div(2 * W * G, RX), ceil_div(2 * H, RY), B), block, 0, stream>>>(
-            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, G, sh, sw);
+        UAPS_LAUNCH(upsample2x_fwd_kernel, dim3(ceil_div(2 * W * G, RX), ceil_div(2 * H, RY), B), block, 0, stream,
+                    reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, G, sh, sw);
     else                // x: upstream gradient [B,2H,2W,C] -> y: [B,H,W,C]
-        upsample2x_bwd_kernel<<<dim3(ceil_div(W * G, RX), ceil_div(H, RY), B), block, 0, stream>>>(
-            reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, G, sh, sw);
+        UAPS_LAUNCH(upsample2x_bwd_kernel, dim3(ceil_div(W * G, RX), ceil_div(H, RY), B), block, 0, stream,
+                    reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, G, sh, sw);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -211,10 +221,10 @@ UAPS_API int uaps_maxpool2_nhwc(const void* x, const void* gy, void* out, int B,
     const int G = C / 8;
     const long long n = (long long)B * (H / 2) * (W / 2) * G;
     if (gy == nullptr)  // forward: x [B,H,W,C] -> out [B,H/2,W/2,C]
-        maxpool2_fwd_kernel<<<rgrid(n), RT, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H, W, G);
+        UAPS_LAUNCH(maxpool2_fwd_kernel, dim3(rgrid(n)), dim3(RT), 0, stream, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), B, H, W, G);
     else                // backward: out = d x [B,H,W,C] (every element written)
-        maxpool2_bwd_kernel<<<rgrid(n), RT, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(gy),
-                                                         reinterpret_cast<uint4*>(out), B, H, W, G);
+        UAPS_LAUNCH(maxpool2_bwd_kernel, dim3(rgrid(n)), dim3(RT), 0, stream, reinterpret_cast<const uint4*>(x),
+                    reinterpret_cast<const uint4*>(gy), reinterpret_cast<uint4*>(out), B, H, W, G);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -224,7 +234,7 @@ UAPS_API int uaps_nchw_f32_to_nhwc_bf16(const float* x, void* out, int B, int C,
     if (Cp % 8 != 0 || Cp < C || B > 65535 || (long long)H * W >= 2147483647LL) return UAPS_ERANGE;
     if (!aligned_to(x, 4) || !aligned_to(out, 16)) return UAPS_EALIGN;
     const int HW = H * W;
-    nchw_f32_to_nhwc_bf16_kernel<<<dim3(ceil_div(HW, RT), B), RT, 0, stream>>>(x, reinterpret_cast<uint4*>(out), C, HW, Cp / 8);
+    UAPS_LAUNCH(nchw_f32_to_nhwc_bf16_kernel, dim3(ceil_div(HW, RT), B), dim3(RT), 0, stream, x, reinterpret_cast<uint4*>(out), C, HW, Cp / 8);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
