@@ -304,6 +304,18 @@ size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks, int fold);
  * swapped: pass cout = W's Cin, cin1 = W's Cout). */
 int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks,
                            int transpose, int fold, cudaStream_t stream);
+/* All layers in one launch: a training iteration re-packs ~124 (layer, layout) pairs after every optimizer step; one launch
+ * each costs 4-5 us.  uaps_conv_pack_plan turns a host job list into a HOST table of n_jobs records of
+ * uaps_conv_pack_job_bytes() bytes; the caller copies the table to device memory once (the addresses in it -- parameters and
+ * packed buffers -- must stay fixed); uaps_conv_pack_run re-packs every layer from the current weights with ONE launch. */
+typedef struct UapsPackJob {
+    const float* w;      /* device, torch layout [cout][cin1+cin2][ks][ks] (as uaps_conv_pack_weights) */
+    void* w_packed;      /* device, uaps_conv_packed_bytes(...) bytes, 16-byte aligned                   */
+    int cout, cin1, cin2, ks, transpose, fold;
+} UapsPackJob;
+size_t uaps_conv_pack_job_bytes(void);
+int uaps_conv_pack_plan(const UapsPackJob* jobs, int n_jobs, void* table_host, int* total_blocks);
+int uaps_conv_pack_run(const void* table_dev, int n_jobs, int total_blocks, cudaStream_t stream);
 /* out2 (nullable): second bf16 NHWC output; output channels >= split (a multiple of 16) are written there
  * at channel (c - split) -- the data gradient of a concat convolution lands in its two consumers' tensors. */
 int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,

@@ -27,6 +27,12 @@ ABI_VERSION = 2
 STEP_USLOTS = 16
 
 
+class PackJobStruct(C.Structure):
+    """Mirror of ``UapsPackJob`` (include/uaps_b200.h)."""
+    _fields_ = [("w", C.c_void_p), ("w_packed", C.c_void_p), ("cout", C.c_int), ("cin1", C.c_int), ("cin2", C.c_int),
+                ("ks", C.c_int), ("transpose", C.c_int), ("fold", C.c_int)]
+
+
 class StepStateStruct(C.Structure):
     """Mirror of ``UapsStepState`` (include/uaps_b200.h): the device-resident per-iteration scalars."""
     _fields_ = [("iter", C.c_uint64), ("key_rank", C.c_uint64), ("key_shared", C.c_uint64), ("adam_step", C.c_uint64),
@@ -70,6 +76,9 @@ _SIGNATURES = {
     "uaps_bn_act_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _d, _u64, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "uaps_conv_packed_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "uaps_conv_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "uaps_conv_pack_job_bytes": (C.c_size_t, []),
+    "uaps_conv_pack_plan": (_i, [_vp, _i, _vp, _vp]),
+    "uaps_conv_pack_run": (_i, [_vp, _i, _i, _vp]),
     "uaps_conv_fprop": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "uaps_conv_fprop_act": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _vp]),
     "uaps_conv_wgrad_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i, _i]),

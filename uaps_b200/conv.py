@@ -210,7 +210,62 @@ class pack_scope:
         return False
 
 
+class WeightPacker:
+    """All conv layers of a model re-packed with ONE launch per iteration (uaps_conv_pack_run) instead of one launch per
+    (layer, layout) -- 124 launches of 4-5 us for UNet_UAPS.
+
+    The first iteration it sees packs layer by layer as usual and records every request; ``finalize()`` turns the record into
+    a device job table; from then on ``run()`` (top of every iteration, after the optimizer has changed the weights) re-packs
+    everything into the same buffers and ``get()`` only hands out the cached ``PackedConv`` objects.  Valid while the
+    parameters' storage stays where it is (parameters re-homed into FlatAdam's flat buffer never move)."""
+
+    def __init__(self):
+        self.entries, self.jobs, self.table, self.total_blocks = {}, [], None, 0
+
+    @property
+    def ready(self) -> bool:
+        return self.table is not None
+
+    def get(self, weight, bias, cin_split, transpose, fold) -> "PackedConv":
+        key = (id(weight), transpose, cin_split, fold)
+        pc = self.entries.get(key)
+        if pc is None:
+            pc = PackedConv(weight, bias, cin_split=cin_split, transpose=transpose, fold=fold)
+            if self.ready:
+                return pc                    # a layout the recorded iteration did not use: packed on the spot, not cached
+            self.entries[key] = pc
+            co, ci = weight.shape[0], weight.shape[1]
+            cout, cin1, cin2 = (ci, co, 0) if transpose else (co, ci if cin_split is None else cin_split,
+                                                              0 if cin_split is None else ci - cin_split)
+            self.jobs.append((weight.detach(), pc.packed, cout, cin1, cin2, pc.ks, int(transpose), fold))
+        return pc
+
+    def finalize(self, device: torch.device) -> None:
+        if self.ready or not self.jobs:
+            return
+        n = len(self.jobs)
+        arr = (L.PackJobStruct * n)()
+        for i, (w, dst, cout, cin1, cin2, ks, tr, fold) in enumerate(self.jobs):
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                return                       # packing goes through a converted copy: keep the per-layer path
+            arr[i] = L.PackJobStruct(w.data_ptr(), dst.data_ptr(), cout, cin1, cin2, ks, tr, fold)
+        import ctypes as C
+        lib = L.lib()
+        host = torch.empty(n * lib.uaps_conv_pack_job_bytes(), dtype=torch.uint8)
+        total = C.c_int(0)
+        L.check(lib.uaps_conv_pack_plan(arr, n, host.data_ptr(), C.byref(total)), "uaps_conv_pack_plan")
+        self.table, self.total_blocks = host.to(device), int(total.value)
+
+    def run(self) -> None:
+        with L.on_device(self.table.device):
+            L.check(L.lib().uaps_conv_pack_run(self.table.data_ptr(), len(self.jobs), self.total_blocks, L.stream_ptr()),
+                    "uaps_conv_pack_run")
+
+
 def packed(weight: torch.Tensor, bias, cin_split=None, transpose: bool = False, fold: int = 1) -> "PackedConv":
+    sc = stepctx.current()
+    if sc is not None and sc.packer is not None:
+        return sc.packer.get(weight, bias, cin_split, transpose, fold)
     if _scope_depth == 0:
         return PackedConv(weight, bias, cin_split=cin_split, transpose=transpose, fold=fold)
     key = (id(weight), transpose, cin_split, fold)

@@ -475,16 +475,44 @@ __device__ __forceinline__ float logical_w(const PackArgs& p, int co, int ci, in
 // channels (same memory).  The virtual conv has Cin' = F*Cin, Cout' = F*Cout and three horizontal taps dj over
 // folded pixels; virtual weight [(b,co)][(a,ci)][r][dj] = W[co][ci][r][s] with s = (dj-1)*F + a - b + 1 when
 // that is a real tap, else 0.  F x more MACs (free: these layers are bandwidth bound), F x wider TMA rows.
+__device__ __forceinline__ void pack_weights_body(const PackArgs& p, long long first, long long stride);
+
 __global__ void pack_weights_kernel(PackArgs p) {
     grid_dep_launch();
     grid_dep_wait();
+    pack_weights_body(p, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// Every layer of the network in ONE launch (uaps_conv_pack_run): a device table holds one PackArgs per (layer, layout)
+// plus the first block of each job; a block finds its job by scanning the (<= a few hundred) starts.  Replaces the 124
+// launches of 4-5 us that packing weights layer by layer costs per training iteration.
+struct PackJob { PackArgs args; int first_block; int n_blocks; };
+__global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
+    grid_dep_launch();
+    grid_dep_wait();
+    __shared__ int s_job;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_jobs - 1;                      // last job whose first_block <= blockIdx.x
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        s_job = lo;
+    }
+    __syncthreads();
+    const PackJob& j = jobs[s_job];
+    pack_weights_body(j.args, (long long)((int)blockIdx.x - j.first_block) * blockDim.x + threadIdx.x,
+                      (long long)j.n_blocks * blockDim.x);
+}
+
+__device__ __forceinline__ void pack_weights_body(const PackArgs& p, long long first, long long stride) {
     const int F = p.fold;
     const int chunks_per_row = p.ck / 8;
     const int chunks0 = F * p.seg_mem[0] / p.ck, chunks1 = p.nseg > 1 ? F * p.seg_mem[1] / p.ck : 0;
     const int iters = (chunks0 + chunks1) * p.ks;
     const int cout_v = F * p.cout_mem;
     const long long total = (long long)p.n_tiles * iters * p.ks * p.n_tile * chunks_per_row;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (long long idx = first; idx < total; idx += stride) {
         long long t = idx;
         const int j = t % chunks_per_row; t /= chunks_per_row;
         const int n = t % p.n_tile; t /= p.n_tile;
@@ -590,8 +618,9 @@ UAPS_API size_t uaps_conv_packed_bytes(int cout, int cin1, int cin2, int ks, int
     return pl.packed_bytes;
 }
 
-UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks, int transpose,
-                                    int fold, cudaStream_t stream) {
+namespace {
+int make_pack_args(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks, int transpose, int fold, PackArgs* out,
+                   int* grid) {
     Plan pl;
     int rc = make_plan(cout, cin1, cin2, ks, fold, &pl);
     if (rc != UAPS_OK) return rc;
@@ -606,8 +635,53 @@ UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, in
     p.cout_mem = fold > 1 ? (cout + 15) / 16 * 16 : pl.n_tiles * pl.n_tile;
     p.fold = fold; p.transpose = transpose;
     const long long total = (long long)pl.packed_bytes / 16;
-    const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    *grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    *out = p;
+    return UAPS_OK;
+}
+}  // namespace
+
+UAPS_API int uaps_conv_pack_weights(const float* w, void* w_packed, int cout, int cin1, int cin2, int ks, int transpose,
+                                    int fold, cudaStream_t stream) {
+    PackArgs p{};
+    int grid = 0;
+    const int rc = make_pack_args(w, w_packed, cout, cin1, cin2, ks, transpose, fold, &p, &grid);
+    if (rc != UAPS_OK) return rc;
     UAPS_LAUNCH(pack_weights_kernel, dim3(grid), dim3(256), 0, stream, p);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}
+
+// ---- all layers in one launch -------------------------------------------------------------------------------
+// uaps_conv_pack_plan fills a HOST table (n_jobs records of uaps_conv_pack_job_bytes() bytes) from the job list; the caller
+// copies it to device memory once (the pointers in it are the parameters' and the packed buffers' device addresses, which
+// must stay fixed -- true for parameters living in a flat buffer); uaps_conv_pack_run then re-packs every layer from the
+// current parameter values with a single launch, e.g. at the top of every training iteration.
+UAPS_API size_t uaps_conv_pack_job_bytes(void) { return sizeof(PackJob); }
+
+UAPS_API int uaps_conv_pack_plan(const UapsPackJob* jobs, int n_jobs, void* table_host, int* total_blocks) {
+    if (jobs == nullptr || table_host == nullptr || total_blocks == nullptr || n_jobs <= 0) return UAPS_EINVAL;
+    PackJob* out = reinterpret_cast<PackJob*>(table_host);
+    int next = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        int grid = 0;
+        const int rc = make_pack_args(jobs[i].w, jobs[i].w_packed, jobs[i].cout, jobs[i].cin1, jobs[i].cin2, jobs[i].ks,
+                                      jobs[i].transpose, jobs[i].fold, &out[i].args, &grid);
+        if (rc != UAPS_OK) return rc;
+        if (grid > 64) grid = 64;                      // many small jobs share the machine: cap one job's blocks
+        out[i].first_block = next;
+        out[i].n_blocks = grid;
+        next += grid;
+    }
+    *total_blocks = next;
+    return UAPS_OK;
+}
+
+UAPS_API int uaps_conv_pack_run(const void* table_dev, int n_jobs, int total_blocks, cudaStream_t stream) {
+    if (table_dev == nullptr || n_jobs <= 0 || total_blocks <= 0) return UAPS_EINVAL;
+    if (!aligned_to(table_dev, 8)) return UAPS_EALIGN;
+    UAPS_LAUNCH(pack_weights_batched_kernel, dim3(total_blocks), dim3(256), 0, stream, reinterpret_cast<const PackJob*>(table_dev),
+                n_jobs);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }

@@ -62,7 +62,7 @@ class DeviceStepState:
 
 
 class StepContext:
-    def __init__(self, device, arena_doubles: int = 1 << 17, state: "DeviceStepState" = None, xchg=None):
+    def __init__(self, device, arena_doubles: int = 1 << 17, state: "DeviceStepState" = None, xchg=None, packer=None):
         self.device = device
         self.arena = torch.zeros(arena_doubles, dtype=torch.float64, device=device)
         self.used = 0
@@ -71,6 +71,7 @@ class StepContext:
         self.stream = None                 # raw cudaStream_t of the iteration, cached for the ~1150 launches (see _lib.stream_ptr)
         self.state = state                 # device-resident scalars (None: host-drawn scalars passed by value)
         self.xchg = xchg                   # this trainer's own LossExchange (device-managed epochs) or None
+        self.packer = packer               # conv.WeightPacker: all layers' weights re-packed by one launch per iteration
         self._seed_calls = self._u_calls = self._xchg_calls = 0
 
     def take(self, n: int) -> torch.Tensor:

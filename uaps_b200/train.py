@@ -39,7 +39,7 @@ import torch
 import torch.distributed as dist
 
 from . import perturb as P
-from .conv import pack_scope
+from .conv import WeightPacker, pack_scope
 from .stepctx import DeviceStepState, StepContext
 from .losses import uaps_supervised_loss, uaps_unlabeled_loss
 from .ramps import get_current_consistency_weight
@@ -279,6 +279,7 @@ class UAPSTrainer:
         self.xchg = None
         self._graphs: Dict[tuple, _Captured] = {}
         self._warm: Dict[tuple, int] = {}
+        self.packer = WeightPacker()                          # one launch re-packs every conv layer's weights per iteration
         want_dev = (self.cfg.device_state and dev.type == "cuda" and getattr(model, "compute", None) == "bf16"
                     and isinstance(self.optimizer, FlatAdam))
         if want_dev and self.world > 1:
@@ -324,7 +325,8 @@ class UAPSTrainer:
         cap = self._graphs.get(key)
         if cap is None:
             n = self._warm.get(key, 0)
-            if n < self.cfg.graph_warmup:                    # lazy initialisation (module loading, allocator) outside the capture
+            if n < max(1, self.cfg.graph_warmup):            # lazy initialisation (module loading, allocator, the weight packer's
+                                                             # recording iteration) outside the capture
                 self._warm[key] = n + 1
                 out = self._device_step(x_l, y_l, x_u)
                 self._iter += 1
@@ -387,9 +389,11 @@ class UAPSTrainer:
         """The iteration with every per-iteration scalar in device memory: a static launch sequence."""
         st, c = self.state, self.cfg
         self.model.train()
-        with pack_scope(), StepContext(x_l.device, state=st, xchg=self.xchg):
+        with pack_scope(), StepContext(x_l.device, state=st, xchg=self.xchg, packer=self.packer):
             st.begin(self.seed_rank, self.seed_shared, self.k, 16, c.consistency1, c.consistency2, c.consistency_rampup,
                      c.iters_per_ramp_epoch, 2 if self.xchg is not None else 0, self.optimizer.betas[0], self.optimizer.betas[1])
+            if self.packer.ready:
+                self.packer.run()                            # the weights changed in the last optimizer step: re-pack all layers
             out_l = self.model(x_l)                                                              # :177
             out_u = self.model(x_u)                                                              # :185
             sup, tce, tdice, ce_k = uaps_supervised_loss(out_l, y_l, group=self.group, step_state=st)      # :194-218
@@ -398,6 +402,7 @@ class UAPSTrainer:
             loss = sup + loss_u                                                                  # :282
             self.grads.zero()                                                                    # :285
             loss.backward()                                                                      # :287
+        self.packer.finalize(x_l.device)                     # (first iteration only: the recorded requests -> device job table)
         self._reduce_gradients()
         # a non-finite loss (an exchange that timed out on a dead peer) must not reach the parameters: the kernel skips
         self.optimizer.step(guard=loss.detach(), use_device_state=True, reducer=self.reducer)    # :292
