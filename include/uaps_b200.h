@@ -247,7 +247,10 @@ int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range, double p
 int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, const void* g_fdrop, uint64_t seed,
                            float noise_range, double p_drop, const float* attention,
                            const uint32_t* smax_enc, float u, void* dx, int B, int C, int64_t HW,
-                           const uint64_t* seed_dev, const float* u_dev, cudaStream_t stream);
+                           const uint64_t* seed_dev, const float* u_dev,
+                           const void* g_extra1, const void* g_extra2, /* nullable: gradients of UNPERTURBED uses of x (the main
+                              decoder's skip connection, the next level's max-pool), added to dx in the same pass */
+                           cudaStream_t stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (utilities/UAPS_unet.py:74-75) and
  * nn.MaxPool2d(2) (:56) on channels-last bf16, C % 8 == 0.

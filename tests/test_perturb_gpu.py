@@ -144,3 +144,30 @@ def test_channels_last_bf16_kernel(shape):
     (yf * cots[2]).sum().backward()
     gf = x.grad.float()
     assert torch.equal(gf * margin, cots[2].float() * (att < thr) * margin)
+
+
+def test_perturb3_nhwc_alias_outputs_fold_every_gradient_into_one_kernel():
+    """aliases=2: two extra outputs that ARE x (for the unperturbed consumers); the backward kernel must return the same dx as
+    autograd's separate accumulation of the five contributions."""
+    from uaps_b200.perturb import perturb3_nhwc
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(3, 32, 24, 16, generator=g, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2)      # channels_last [3,16,32,24]
+    cots = [torch.randn(3, 32, 24, 16, generator=g, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2) for _ in range(5)]
+    xa = x.clone().requires_grad_(True)
+    outs = perturb3_nhwc(xa, seed=11, u=0.8, aliases=2)
+    assert len(outs) == 5 and outs[3].data_ptr() == xa.data_ptr() and torch.equal(outs[4], xa.detach())
+    torch.autograd.backward(outs, cots)
+    xb = x.clone().requires_grad_(True)
+    ref = perturb3_nhwc(xb, seed=11, u=0.8)
+    for o, r in zip(outs[:3], ref):
+        assert torch.equal(o, r)
+    torch.autograd.backward(ref, cots[:3])
+    want = xb.grad.float() + cots[3].float() + cots[4].float()
+    assert (xa.grad.float() - want).abs().max().item() <= 2e-2 * want.abs().max().item()     # one bf16 rounding instead of three
+    # a single alias and a single perturbed copy (the K = 5 ablation's extra decoder uses outputs=(True, False, False))
+    xc = x.clone().requires_grad_(True)
+    o1 = perturb3_nhwc(xc, seed=5, u=0.8, outputs=(True, False, False), aliases=1)
+    assert o1[1] is None and o1[2] is None and len(o1) == 4
+    (o1[0].float().sum() + 2.0 * o1[3].float().sum()).backward()
+    assert torch.isfinite(xc.grad.float()).all()

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
                                                            const float* __restrict__ attention, const uint32_t* __restrict__ smax_enc,
                                                            float u, uint4* __restrict__ y_noise, uint4* __restrict__ y_drop,
                                                            uint4* __restrict__ y_fdrop, uint4* __restrict__ dx, int G, long long HW, int B,
-                                                           const uint64_t* __restrict__ seed_dev, const float* __restrict__ u_dev) {
+                                                           const uint64_t* __restrict__ seed_dev, const float* __restrict__ u_dev,
+                                                           const uint4* __restrict__ g_extra1, const uint4* __restrict__ g_extra2) {
     grid_dep_launch();
     grid_dep_wait();
     if (seed_dev != nullptr) seed += *seed_dev;       // device-resident step state (uaps_step_begin)
@@ -134,6 +135,18 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = fmaf(g[i], m, o[i]);
             }
+            // gradients of the UNPERTURBED uses of the same feature map (main decoder's skip connection, the next level's
+            // max-pool): summed here instead of by two separate accumulation kernels (each a read-read-write pass)
+            if (g_extra1 != nullptr) {
+                unpack8(__ldg(g_extra1 + t), g);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += g[i];
+            }
+            if (g_extra2 != nullptr) {
+                unpack8(__ldg(g_extra2 + t), g);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += g[i];
+            }
             dx[t] = pack8(o);
         }
     }
@@ -177,7 +190,8 @@ UAPS_API int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range,
     UAPS_LAUNCH(perturb3_nhwc_kernel<false>, dim3(grid1d(HW * (C / 8) * B)), dim3(PT), 0, stream,
         reinterpret_cast<const uint4*>(x), (const uint4*)nullptr, (const uint4*)nullptr, (const uint4*)nullptr, seed, noise_range,
         (float)p_drop, (float)(1.0 / (double)pk), attention, smax_enc, u, reinterpret_cast<uint4*>(y_noise),
-        reinterpret_cast<uint4*>(y_drop), reinterpret_cast<uint4*>(y_fdrop), (uint4*)nullptr, C / 8, (long long)HW, B, seed_dev, u_dev);
+        reinterpret_cast<uint4*>(y_drop), reinterpret_cast<uint4*>(y_fdrop), (uint4*)nullptr, C / 8, (long long)HW, B, seed_dev, u_dev,
+        (const uint4*)nullptr, (const uint4*)nullptr);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
@@ -185,17 +199,19 @@ UAPS_API int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range,
 UAPS_API int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, const void* g_fdrop, uint64_t seed,
                                     float noise_range, double p_drop, const float* attention, const uint32_t* smax_enc,
                                     float u, void* dx, int B, int C, int64_t HW, const uint64_t* seed_dev, const float* u_dev,
-                                    cudaStream_t stream) {
+                                    const void* g_extra1, const void* g_extra2, cudaStream_t stream) {
     if (dx == nullptr || B <= 0 || HW <= 0) return UAPS_EINVAL;
     if (g_fdrop != nullptr && (attention == nullptr || smax_enc == nullptr)) return UAPS_EINVAL;
-    if (g_noise == nullptr && g_drop == nullptr && g_fdrop == nullptr) return UAPS_EINVAL;
+    if (g_noise == nullptr && g_drop == nullptr && g_fdrop == nullptr && g_extra1 == nullptr && g_extra2 == nullptr) return UAPS_EINVAL;
+    if (!aligned_to(g_extra1, 16) || !aligned_to(g_extra2, 16)) return UAPS_EALIGN;
     if (!valid_g(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
     if (!aligned_to(dx, 16) || !aligned_to(g_noise, 16) || !aligned_to(g_drop, 16) || !aligned_to(g_fdrop, 16)) return UAPS_EALIGN;
     const float pk = (float)(1.0 - p_drop);
     UAPS_LAUNCH(perturb3_nhwc_kernel<true>, dim3(grid1d(HW * (C / 8) * B)), dim3(PT), 0, stream,
         (const uint4*)nullptr, reinterpret_cast<const uint4*>(g_noise), reinterpret_cast<const uint4*>(g_drop),
         reinterpret_cast<const uint4*>(g_fdrop), seed, noise_range, (float)p_drop, (float)(1.0 / (double)pk), attention, smax_enc, u,
-        (uint4*)nullptr, (uint4*)nullptr, (uint4*)nullptr, reinterpret_cast<uint4*>(dx), C / 8, (long long)HW, B, seed_dev, u_dev);
+        (uint4*)nullptr, (uint4*)nullptr, (uint4*)nullptr, reinterpret_cast<uint4*>(dx), C / 8, (long long)HW, B, seed_dev, u_dev,
+        reinterpret_cast<const uint4*>(g_extra1), reinterpret_cast<const uint4*>(g_extra2));
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }

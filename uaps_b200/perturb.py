@@ -228,7 +228,7 @@ def perturb3(x: torch.Tensor, *, noise: Optional[torch.Tensor] = None, keep: Opt
 # ---- channels-last bf16 variant (bf16 / tcgen05 model path) ------------------------------------------
 class _Perturb3NhwcFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, seed, rng, p, u, seed_dev, u_dev, n_out):
+    def forward(ctx, x, seed, rng, p, u, seed_dev, u_dev, n_out, n_alias):
         L.require_cuda(x)
         if x.dtype != torch.bfloat16 or not x.is_contiguous(memory_format=torch.channels_last):
             raise RuntimeError("perturb3_nhwc expects a channels_last bf16 [B,C,H,W] tensor")
@@ -249,29 +249,39 @@ class _Perturb3NhwcFn(torch.autograd.Function):
                                            seed_dev, u_dev, L.stream_ptr()), "uaps_perturb3_nhwc")
         ctx.save_for_backward(attention, smax)
         ctx.args = (seed, rng, p, u, seed_dev, u_dev, n_out[2])
-        return tuple(ys)
+        # n_alias extra outputs that ARE x (views): the unperturbed consumers of the feature map take these, so x has this
+        # node as its only consumer and all of its gradient contributions are summed in the one backward kernel
+        return tuple(ys) + tuple(x.view_as(x) for _ in range(n_alias))
 
     @staticmethod
-    def backward(ctx, g_noise, g_drop, g_fdrop):
+    def backward(ctx, g_noise, g_drop, g_fdrop, *g_alias):
         attention, smax = ctx.saved_tensors
         seed, rng, p, u, seed_dev, u_dev, has_stats = ctx.args
-        gs = [None if g is None else g.contiguous(memory_format=torch.channels_last) for g in (g_noise, g_drop, g_fdrop)]
-        ref = next(g for g in gs if g is not None)
+        cl = lambda g: None if g is None else g.contiguous(memory_format=torch.channels_last)
+        gs = [cl(g) for g in (g_noise, g_drop, g_fdrop)]
+        extra = [cl(g) for g in g_alias if g is not None]
+        while len(extra) > 2:                                 # the kernel takes two; more than that never happens in UNet_UAPS
+            extra = [extra[0] + extra[1]] + extra[2:]
+        extra += [None] * (2 - len(extra))
+        ref = next(g for g in gs + extra if g is not None)
         B, C, H, W = ref.shape
         dx = torch.empty_like(ref)
         with L.on_device(ref.device):
             L.check(L.lib().uaps_perturb3_nhwc_bwd(*[None if g is None else g.data_ptr() for g in gs], seed, rng, p,
                                                    attention.data_ptr() if has_stats else None,
                                                    smax.data_ptr() if has_stats else None, u, dx.data_ptr(), B, C, H * W,
-                                                   seed_dev, u_dev, L.stream_ptr()), "uaps_perturb3_nhwc_bwd")
-        return (dx,) + (None,) * 7
+                                                   seed_dev, u_dev, *[None if g is None else g.data_ptr() for g in extra],
+                                                   L.stream_ptr()), "uaps_perturb3_nhwc_bwd")
+        return (dx,) + (None,) * 8
 
 
 def perturb3_nhwc(x: torch.Tensor, *, u: Optional[float] = None, seed: Optional[int] = None,
-                  uniform_range: float = 0.3, p: float = 0.5, outputs=(True, True, True)):
+                  uniform_range: float = 0.3, p: float = 0.5, outputs=(True, True, True), aliases: int = 0):
     """Channels-last bf16 ``perturb3``: (FeatureNoise, Dropout, FeatureDropout) of one feature map in one pass.
     ``outputs``: which of the three copies to produce (None for the others) -- a 4th / 5th auxiliary decoder (the K = 5
     ablation) calls it again for ONE more copy of the perturbation family it re-uses, with a fresh draw.
+    ``aliases``: that many extra outputs that are x itself -- hand them to the UNPERTURBED consumers of x (main decoder, next
+    level's max-pool) and the backward kernel sums their gradients too, instead of autograd's separate accumulation passes.
     Inside a device-resident iteration (``stepctx.current().state``) the Philox key and the threshold u come from the
     device step state; otherwise they are drawn from ``uaps_b200.perturb.generator`` on the host."""
     from . import stepctx
@@ -289,4 +299,4 @@ def perturb3_nhwc(x: torch.Tensor, *, u: Optional[float] = None, seed: Optional[
         _mix_rank_once()
         u = float(generator.uniform(0.7, 0.9))
     return _Perturb3NhwcFn.apply(x, int(seed), float(uniform_range), float(p), float(np.float32(u)), seed_dev, u_dev,
-                                 tuple(bool(o) for o in outputs))
+                                 tuple(bool(o) for o in outputs), int(aliases))

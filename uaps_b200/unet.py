@@ -134,10 +134,16 @@ class UNet_UAPS(nn.Module):
             y = y * (keep.to(y.dtype) * (1.0 / (1.0 - p_drop)))
         return F.leaky_relu(b4(conv_bf16(y, c4.weight, c4.bias, bias_grad=bg)), 0.01)
 
-    def _encode16(self, x, enc_keep):
+    def _encode16(self, x, enc_keep, perturbed=None):
+        """perturbed: a list to receive, per level, the (noise, dropout, feature-dropout) copies of the level's feature map
+        (rows a2-a4, one fused Philox kernel per level).  The unperturbed consumers of the feature map -- the main decoder
+        and the next level's max-pool -- then take ALIAS outputs of that kernel's autograd node, so the feature map's whole
+        gradient (three perturbed decoders + main decoder + pool) is summed by the one backward kernel instead of by
+        autograd's separate accumulation passes."""
         B, C, H, W = x.shape
         x16 = to_nhwc_bf16(x).permute(0, 3, 1, 2)             # logical NCHW, channels-last memory, 16-padded
         feats, cur = [], x16
+        live = tuple(a <= self.n_aux for a in (1, 2, 3))
         for lvl in range(5):
             if lvl == 0:
                 blk = self.encoder.in_conv
@@ -145,7 +151,13 @@ class UNet_UAPS(nn.Module):
                 cur = maxpool2(cur)
                 blk = self.encoder.get_submodule(f"down{lvl}").maxpool_conv.get_submodule("1")
             cur = self._block16(cur, blk, ENC_DROPOUT[lvl], None if enc_keep is None else enc_keep[lvl])
-            feats.append(cur)
+            if perturbed is not None:
+                outs = P.perturb3_nhwc(cur, outputs=live, aliases=2 if lvl < 4 else 1)
+                perturbed.append(outs[:3])
+                feats.append(outs[3])                          # for the main decoder
+                cur = outs[4] if lvl < 4 else outs[3]          # for the next level's max-pool
+            else:
+                feats.append(cur)
         return feats
 
     def _decode16(self, feats, dec):
@@ -157,12 +169,9 @@ class UNet_UAPS(nn.Module):
         return conv_bf16(x, dec.out_conv.weight, dec.out_conv.bias, nchw_f32_out=True)
 
     def _forward16(self, x, rand):
-        feats = self._encode16(x, None if rand is None else rand["enc_keep"])
+        fused = [] if (rand is None and self.n_aux > 0) else None     # one fused Philox kernel per level (rows a2-a4)
+        feats = self._encode16(x, None if rand is None else rand["enc_keep"], perturbed=fused)
         outs = [self._decode16(feats, self.main_decoder)]
-        fused = None
-        if rand is None and self.n_aux > 0:                    # one fused Philox kernel per level (rows a2-a4)
-            live = tuple(a <= self.n_aux for a in (1, 2, 3))
-            fused = [P.perturb3_nhwc(f, outputs=live) for f in feats]
         for a in range(1, self.n_aux + 1):
             kind = _AUX_KINDS[(a - 1) % 3]
             if fused is not None and a <= 3:
