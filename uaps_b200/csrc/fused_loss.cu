@@ -49,8 +49,12 @@ int pick_vec(const float* const* z, float* const* o, int K, int64_t HW) {
 // the torch-order ones.  UAPS_LOSS_IMPL=<0..2> overrides the choice (tuning knob, not part of the ABI).
 int pick_impl(int avail_vec, int flags, bool pass2) {
     static const int forced = [] { const char* e = getenv("UAPS_LOSS_IMPL"); return e ? atoi(e) : -1; }();
+    static const int forced_p1 = [] { const char* e = getenv("UAPS_LOSS_P1_IMPL"); return e ? atoi(e) : -1; }();   // pass 1 only
     if (flags & UAPS_LOSS_EXACT) return IMPL_EXACT;
     if (avail_vec < 2) return IMPL_SCALAR;
+    if (!pass2 && forced_p1 >= 0 && forced_p1 != IMPL_EXACT && forced_p1 <= IMPL_VEC4 && (forced_p1 != IMPL_VEC4 || avail_vec >= 4) &&
+        (forced_p1 != IMPL_VEC4_PF || avail_vec >= 4))
+        return forced_p1;
     if (forced >= 0 && forced <= IMPL_SCALAR) return forced;
     if (avail_vec < 4) return IMPL_VEC2_PF;
     return pass2 ? IMPL_VEC2_PF : IMPL_VEC4_PF;

@@ -751,7 +751,7 @@ loss_pass2_kernel(const __grid_constant__ LossArgs a, const float* __restrict__ 
 // kernels beat both the plain ones (first-use stall on the K*C loads was 36% of all warp stall
 // samples) and a cp.async.bulk/mbarrier shared-memory ring (which removed that stall but lost the
 // cross-pixel ILP the per-thread vector gives); pass 1 likes 4 pixels/thread, pass 2 two.
-enum LossImpl { IMPL_VEC4_PF = 0, IMPL_VEC2_PF = 1, IMPL_SCALAR = 2, IMPL_EXACT = 3 };
+enum LossImpl { IMPL_VEC4_PF = 0, IMPL_VEC2_PF = 1, IMPL_SCALAR = 2, IMPL_EXACT = 3, IMPL_VEC2 = 4, IMPL_VEC4 = 5 };
 
 __host__ __device__ constexpr bool has_vec4(int K, int C) { return K * C <= 16; }
 __host__ __device__ constexpr bool has_vec2(int K, int C) { return K * C <= 24; }
@@ -798,6 +798,13 @@ inline int launch_kc(int impl, bool sup, bool pass2, const LossArgs& a, float* p
          : (a.w_dev != nullptr ? launch_reg<K, C, VEC, false, EXACT, PF, true>(pass2, a, partials, sc, go, nblocks, st) \
                                : launch_reg<K, C, VEC, false, EXACT, PF, false>(pass2, a, partials, sc, go, nblocks, st)))
     if (impl == IMPL_EXACT) return UAPS_RUN(1, true, false);
+#ifdef UAPS_LOSS_EXTRA_VARIANTS       // tuning builds only: vector kernels WITHOUT the register prefetch (3 CTAs per SM instead of 2).
+    // Measured on B200, K=4 C=4 64x256x256, pass 1 + fold: VEC4+prefetch (default, 2 CTAs/SM) 82.1 us | VEC2 no prefetch 93.3 |
+    // VEC2+prefetch 108.2 | VEC4 no prefetch (spills) 108.9 | scalar 114.7 -- more resident warps do not help: the kernel
+    // needs the 4-pixel instruction-level parallelism inside a thread, not thread-level parallelism.
+    if constexpr (has_vec2(K, C)) { if (impl == IMPL_VEC2) return UAPS_RUN(2, false, false); }
+    if constexpr (has_vec4(K, C)) { if (impl == IMPL_VEC4) return UAPS_RUN(4, false, false); }
+#endif
     if constexpr (has_vec4(K, C)) { if (impl == IMPL_VEC4_PF) return UAPS_RUN(4, false, true); }
     if constexpr (has_vec2(K, C)) { if (impl == IMPL_VEC4_PF || impl == IMPL_VEC2_PF) return UAPS_RUN(2, false, true); }
     return UAPS_RUN(1, false, false);
