@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(BT, MINB) bn_act_bwd_kernel(const uint4* __res
 }
 
 inline int bn_grid(long long chunks, int ctas_per_sm = 8) {
-    long long want = ceil_div<long long>(chunks, BT), cap = (long long)device_info().sm_count * ctas_per_sm;
+    static const int mult = [] { const char* e = getenv("UAPS_BN_GRID_MULT"); return e ? atoi(e) : 1; }();   // A/B knob: waves per launch
+    long long want = ceil_div<long long>(chunks, BT), cap = (long long)device_info().sm_count * ctas_per_sm * (mult > 0 ? mult : 1);
     return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 // the reducing kernels are launched in clusters: whole clusters only (surplus CTAs contribute zeros)

@@ -33,81 +33,137 @@ __device__ __forceinline__ void src_coord(int o, float scale, int in_size, int& 
     l1 = s - (float)i0;
 }
 
-// Both resampling kernels use a 3-D grid -- x: 16-byte chunks along a row (pixel * G + g), y: rows in bands of
-// RY, z: image -- so the index math is 32-bit (the 1-D version spent most of its time in 64-bit div/mod) and a CTA
-// covers a 2-D patch: the 2 x 2 (forward) / up-to-4 x 4 (backward) stencils of neighbouring threads overlap in L1.
+// Both resampling kernels use a 3-D grid -- x: 16-byte chunks along a row (pixel * G + g), y: INPUT rows in bands of
+// RY, z: image -- so the index math is 32-bit and a CTA covers a 2-D patch whose stencils overlap in L1.
+// Round 2: ncu showed both kernels instruction-issue bound (75-77 % issue-active at 1.8-2.3 TB/s,
+// profiles/r02_kernels_ncu_full.txt), so the per-output instruction count was cut:
+//   * packed fp32x2 arithmetic (FFMA2 / FMUL2, sm_100): a bf16x2 pair converts straight into a float2 and the
+//     interpolation runs on pairs -- half the FMA-pipe instructions, IEEE per lane (results unchanged);
+//   * forward: a thread produces the TWO output rows 2k, 2k+1 of its column; their source rows are always drawn from
+//     {y0(2k), y1(2k), y1(2k+1)} (checked exhaustively in fp32 for every size up to 1024), so three horizontally
+//     interpolated rows serve both outputs: 6 loads and 40 packed operations per 2 outputs instead of 8 and 96 scalar;
+//   * backward: the outputs that tap input i are exactly o in [2i-1, 2i+2] (checked the same way): 4 x 4 candidates instead
+//     of 6 x 6 with per-candidate branches, and their weights come from a small shared-memory table computed once per CTA.
 constexpr int RX = 32, RY = 8;            // CTA = 32 chunks x 8 rows = 256 threads
+
+__device__ __forceinline__ void unpack4(const uint4& r, float2 (&v)[4]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __bfloat1622float2(h[i]);
+}
+__device__ __forceinline__ uint4 pack4(const float2 (&v)[4]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __float22bfloat162_rn(v[i]);
+    return r;
+}
+// horizontally interpolated row: hx * left + lx * right (the rounding order of the scalar expression it replaces)
+__device__ __forceinline__ void hrow(const uint4* __restrict__ row, unsigned off0, unsigned off1, float2 hx, float2 lx, float2 (&h)[4]) {
+    float2 a[4], c[4];
+    unpack4(__ldg(row + off0), a);
+    unpack4(__ldg(row + off1), c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __ffma2_rn(c[i], lx, __fmul2_rn(a[i], hx));
+}
 
 __global__ void __launch_bounds__(RT) upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W,
                                                             int G, float sh, float sw) {
     grid_dep_launch();
     grid_dep_wait();
-    const int OH = 2 * H, OW = 2 * W;
-    const unsigned col = blockIdx.x * RX + threadIdx.x;
-    const int oy = blockIdx.y * RY + threadIdx.y;
-    if (col >= (unsigned)OW * G || oy >= OH) return;
+    const int OW = 2 * W;
+    const unsigned col = blockIdx.x * RX + threadIdx.x;           // output chunk column: ox * G + g
+    const int k = blockIdx.y * RY + threadIdx.y;                  // input row band: output rows 2k and 2k + 1
+    if (col >= (unsigned)OW * G || k >= H) return;
     const int ox = col / G, g = col - ox * G;
-    int y0, y1, x0, x1; float ly, lx;
-    src_coord(oy, sh, H, y0, y1, ly);
-    src_coord(ox, sw, W, x0, x1, lx);
-    const uint4* xb = x + (size_t)blockIdx.z * H * W * G;
-    float a[8], c[8], d[8], e[8], o[8];
-    unpack8(__ldg(xb + ((size_t)y0 * W + x0) * G + g), a);
-    unpack8(__ldg(xb + ((size_t)y0 * W + x1) * G + g), c);
-    unpack8(__ldg(xb + ((size_t)y1 * W + x0) * G + g), d);
-    unpack8(__ldg(xb + ((size_t)y1 * W + x1) * G + g), e);
-    const float hy = 1.f - ly, hx = 1.f - lx;
+    int x0, x1, y0a, y1a, y0b, y1b; float lxs, lya, lyb;
+    src_coord(ox, sw, W, x0, x1, lxs);
+    src_coord(2 * k, sh, H, y0a, y1a, lya);                       // warp-uniform (a warp spans x only)
+    src_coord(2 * k + 1, sh, H, y0b, y1b, lyb);
+    const uint4* xb = x + (size_t)blockIdx.z * H * W * G + g;
+    const unsigned o0 = (unsigned)x0 * G, o1 = (unsigned)x1 * G, rowp = (unsigned)W * G;
+    const float2 lx = make_float2(lxs, lxs), hx = make_float2(1.f - lxs, 1.f - lxs);
+    float2 h0[4], h1[4], h2[4], o[4];
+    hrow(xb + (size_t)y0a * rowp, o0, o1, hx, lx, h0);
+    hrow(xb + (size_t)y1a * rowp, o0, o1, hx, lx, h1);
+    {
+        const float2 ly = make_float2(lya, lya), hy = make_float2(1.f - lya, 1.f - lya);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = hy * (hx * a[i] + lx * c[i]) + ly * (hx * d[i] + lx * e[i]);
-    y[((size_t)blockIdx.z * OH + oy) * OW * G + col] = pack8(o);
+        for (int i = 0; i < 4; ++i) o[i] = __ffma2_rn(h1[i], ly, __fmul2_rn(h0[i], hy));
+        y[((size_t)blockIdx.z * 2 * H + 2 * k) * OW * G + col] = pack4(o);
+    }
+    // second output row: its upper tap is y0a or y1a (always), its lower tap y1a or a new row
+    if (y1b != y1a) hrow(xb + (size_t)y1b * rowp, o0, o1, hx, lx, h2);
+    {
+        const float2 ly = make_float2(lyb, lyb), hy = make_float2(1.f - lyb, 1.f - lyb);
+        const bool up_is_a0 = (y0b == y0a), lo_is_a1 = (y1b == y1a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 up = up_is_a0 ? h0[i] : h1[i];
+            const float2 lo = lo_is_a1 ? h1[i] : h2[i];
+            o[i] = __ffma2_rn(lo, ly, __fmul2_rn(up, hy));
+        }
+        y[((size_t)blockIdx.z * 2 * H + 2 * k + 1) * OW * G + col] = pack4(o);
+    }
 }
 
-// weight of output index o onto input index i along one axis (0 when o's two taps miss i)
+// weight of output index o onto input index i along one axis (0 when o's two taps miss i or o is out of range)
 __device__ __forceinline__ float tap_weight(int o, int i, float scale, int in_size) {
+    if (o < 0 || o >= 2 * in_size) return 0.f;
     int i0, i1; float l1;
     src_coord(o, scale, in_size, i0, i1, l1);
     return (i0 == i ? 1.f - l1 : 0.f) + (i1 == i ? l1 : 0.f);
 }
 
-// gather backward: input pixel (iy, ix) collects from the outputs whose stencil touches it.  Output o taps
-// floor(o * r) and its successor, r = (in-1)/(2in-1) in [1/3, 1/2): the candidates of input i are o in
-// [2i-2, 2i+3] (the fp32 evaluation of o * r is the forward's, so borderline taps land where the forward put them).
-constexpr int NCAND = 6;
+// gather backward: input pixel (iy, ix) collects from the outputs whose stencil touches it: o in [2i-1, 2i+2] per axis
+// (the fp32 evaluation of o * r is the forward's, so borderline taps land where the forward put them).
+constexpr int NCAND = 4;
 __global__ void __launch_bounds__(RT) upsample2x_bwd_kernel(const uint4* __restrict__ gy, uint4* __restrict__ gx, int H, int W,
                                                             int G, float sh, float sw) {
+    __shared__ float s_wy[RY][NCAND];
+    __shared__ float s_wx[RX][NCAND];                             // one entry per pixel column of the CTA (<= RX when G = 1)
     grid_dep_launch();
     grid_dep_wait();
     const int OH = 2 * H, OW = 2 * W;
+    const int t = threadIdx.y * RX + threadIdx.x;
+    const int px0 = (blockIdx.x * RX) / G;                        // first pixel column of this CTA
+    if (t < RY * NCAND) {
+        const int r = t / NCAND, a = t % NCAND, iy = blockIdx.y * RY + r;
+        s_wy[r][a] = iy < H ? tap_weight(2 * iy - 1 + a, iy, sh, H) : 0.f;
+    } else if (t >= 64 && t < 64 + RX * NCAND) {
+        const int q = (t - 64) / NCAND, b = (t - 64) % NCAND, ix = px0 + q;
+        s_wx[q][b] = ix < W ? tap_weight(2 * ix - 1 + b, ix, sw, W) : 0.f;
+    }
+    __syncthreads();
     const unsigned col = blockIdx.x * RX + threadIdx.x;
     const int iy = blockIdx.y * RY + threadIdx.y;
     if (col >= (unsigned)W * G || iy >= H) return;
     const int ix = col / G, g = col - ix * G;
     float wy[NCAND], wx[NCAND];
 #pragma unroll
-    for (int k = 0; k < NCAND; ++k) {
-        const int oy = 2 * iy - 2 + k, ox = 2 * ix - 2 + k;
-        wy[k] = (oy >= 0 && oy < OH) ? tap_weight(oy, iy, sh, H) : 0.f;
-        wx[k] = (ox >= 0 && ox < OW) ? tap_weight(ox, ix, sw, W) : 0.f;
-    }
-    float acc[8];
+    for (int a = 0; a < NCAND; ++a) { wy[a] = s_wy[threadIdx.y][a]; wx[a] = s_wx[ix - px0][a]; }
+    float2 acc[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
     const uint4* gb = gy + (size_t)blockIdx.z * OH * OW * G + g;
 #pragma unroll
     for (int a = 0; a < NCAND; ++a) {
-        if (wy[a] == 0.f) continue;
-        const uint4* row = gb + (size_t)(2 * iy - 2 + a) * OW * G;
+        int oy = 2 * iy - 1 + a;
+        oy = oy < 0 ? 0 : (oy >= OH ? OH - 1 : oy);               // out-of-range candidates have zero weight: clamp the address
+        const uint4* row = gb + (size_t)oy * OW * G;
 #pragma unroll
         for (int b = 0; b < NCAND; ++b) {
-            if (wx[b] == 0.f) continue;
-            float v[8];
-            unpack8(__ldg(row + (size_t)(2 * ix - 2 + b) * G), v);
+            int ox = 2 * ix - 1 + b;
+            ox = ox < 0 ? 0 : (ox >= OW ? OW - 1 : ox);
+            float2 v[4];
+            unpack4(__ldg(row + (unsigned)ox * G), v);
             const float w = wy[a] * wx[b];
+            const float2 w2 = make_float2(w, w);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+            for (int i = 0; i < 4; ++i) acc[i] = __ffma2_rn(v[i], w2, acc[i]);
         }
     }
-    gx[((size_t)blockIdx.z * H + iy) * W * G + col] = pack8(acc);
+    gx[((size_t)blockIdx.z * H + iy) * W * G + col] = pack4(acc);
 }
 
 // [B,C,H,W] fp32 (NCHW) -> [B,H,W,Cp] bf16 (channels-last, channels C..Cp-1 zero): the network input and the
@@ -205,7 +261,7 @@ UAPS_API int uaps_upsample2x_nhwc(const void* x, void* y, int B, int H, int W, i
     if (B > 65535 || ceil_div(2 * H, RY) > 65535) return UAPS_ERANGE;
     const dim3 block(RX, RY);
     if (!backward)      // x: [B,H,W,C] -> y: [B,2H,2W,C]
-        UAPS_LAUNCH(upsample2x_fwd_kernel, dim3(ceil_div(2 * W * G, RX), ceil_div(2 * H, RY), B), block, 0, stream,
+        UAPS_LAUNCH(upsample2x_fwd_kernel, dim3(ceil_div(2 * W * G, RX), ceil_div(H, RY), B), block, 0, stream,
                     reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, G, sh, sw);
     else                // x: upstream gradient [B,2H,2W,C] -> y: [B,H,W,C]
         UAPS_LAUNCH(upsample2x_bwd_kernel, dim3(ceil_div(W * G, RX), ceil_div(H, RY), B), block, 0, stream,
