@@ -47,15 +47,28 @@ __global__ void __launch_bounds__(PT) fdrop_stats_nhwc_kernel(const uint4* __res
     __shared__ float s_m[PT / kWarp];
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         float mx = -INFINITY;
-        for (long long t = (long long)blockIdx.x * PT + threadIdx.x; t < chunks_per_sample; t += (long long)gridDim.x * PT) {
+        const uint4* xs = x + (size_t)b * chunks_per_sample;
+        const long long stride = (long long)gridDim.x * PT;
+        auto use = [&](long long t, const uint4& r) {
             float v[8];
-            unpack8(__ldg(x + (size_t)b * chunks_per_sample + t), v);
+            unpack8(r, v);
             float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
             for (int o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);     // G threads of a pixel are adjacent lanes
             s *= invC;
             if ((t % G) == 0) attention[(size_t)b * HW + t / G] = s;
             mx = fmaxf(mx, s);
+        };
+        // four independent 16-byte loads in flight per thread (one per iteration left HBM under-subscribed: 2.4 TB/s);
+        // chunks_per_sample and the strides are multiples of 32, so every warp takes the same path and the shuffles stay whole
+        long long t = (long long)blockIdx.x * PT + threadIdx.x;
+        for (; t + 3 * stride < chunks_per_sample; t += 4 * stride) {
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = __ldg(xs + t + u * stride);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) use(t + u * stride, r[u]);
         }
+        for (; t < chunks_per_sample; t += stride) use(t, __ldg(xs + t));
         mx = warp_max(mx);
         if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = mx;
         __syncthreads();
