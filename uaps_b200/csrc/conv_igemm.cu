@@ -302,7 +302,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
                     for (int ch = 0; ch < a.chunks[seg]; ++ch) {
                         for (int s = 0; s < a.ks; s += s_per_it, ++it, ++itg) {
                             const int st = itg % a.stages;
-                            mbar_wait(empty_bar + st, ((itg / a.stages) & 1) ^ 1);
+                            mbar_wait_relaxed(empty_bar + st, ((itg / a.stages) & 1) ^ 1);
                             unsigned char* sa = stage0 + (size_t)st * stage_bytes;
                             mbar_expect_tx(full_bar + st, a_bytes + (a.resident ? 0 : b_bytes));
                             // xhalo: one box [18][10][CK] starting one pixel left of the tile; else one box per tap s
@@ -379,7 +379,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
             tx += s_tx; if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
             ty += s_ty; if (ty >= a.tiles_y) { ty -= a.tiles_y; ++n_img; }
             n_img += s_n;
-            mbar_wait(acc_full + buf, (tcount >> 1) & 1);
+            mbar_wait_relaxed(acc_full + buf, (tcount >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int j = 0; j < a.n_tile / 16; ++j) {
                 float v[16];

@@ -34,6 +34,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
     }
 }
+// Wait with back-off for the warps that are NOT on the critical path (the four epilogue warps, the TMA producer): each
+// failed try_wait is followed by a nanosleep, so a waiting warp polls every few hundred cycles instead of every ~80 and
+// leaves the issue slots to the warps that have work (ncu, 16-channel conv: BRA + SYNCS + YIELD of the wait loops were
+// 38 % of all executed instructions of a kernel whose issue slots are 60-70 % busy).  MEASURED on B200 with 200 ns
+// (profiles/r02 run 29): no change on any layer (80.6 vs 80.2 us on 16->16 @256x256) -- like the try_wait hint above, it
+// shows the kernel is not limited by issue slots but by the tensor core's shared-memory operand fetch.
+// Off by default (0 = the plain retry loop); -DUAPS_MBAR_SLEEP_NS=200 builds the back-off.
+#ifndef UAPS_MBAR_SLEEP_NS
+#define UAPS_MBAR_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+#if UAPS_MBAR_SLEEP_NS > 0
+        __nanosleep(UAPS_MBAR_SLEEP_NS);
+#endif
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
