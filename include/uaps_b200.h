@@ -279,7 +279,10 @@ int uaps_bn_act_nhwc(const void* y, const double* sum, const double* sumsq, cons
                      const float* beta, float* running_mean, float* running_var, float momentum,
                      float eps, float slope, double p_drop, uint64_t seed, void* out,
                      float* save_mean, float* save_rstd, int64_t npix, int C,
-                     const uint64_t* seed_dev /* nullable: *seed_dev is added to seed */, cudaStream_t stream);
+                     const uint64_t* seed_dev /* nullable: *seed_dev is added to seed */,
+                     int nrep /* 1: sum / sumsq are the batch sums; n > 1: n replicas [sum[C] | sumsq[C]] (stride 2C doubles from
+                                 `sum` resp. `sumsq`) whose sum they are, as uaps_conv_fprop_bn leaves them */,
+                     cudaStream_t stream);
 int uaps_bn_act_bwd_nhwc(const void* g_out, const void* y, const float* gamma, const float* beta,
                          const float* save_mean, const float* save_rstd, float slope, double p_drop,
                          uint64_t seed, double* sum_g, double* sum_gx, void* dy,
@@ -325,6 +328,14 @@ int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride
                     const float* bias, void* out, int out_c_stride, int out_nchw_f32,
                     int B, int H, int W, int cin1, int cin2, int cout, int ks,
                     void* out2, int out2_c_stride, int split, int fold, cudaStream_t stream);
+/* conv + bias -> bf16 NHWC (as uaps_conv_fprop without out2 / fold / NCHW) AND the BatchNorm batch statistics of that
+ * output from the accumulators, in the same kernel (utilities/UAPS_unet.py:36-38, 41-42: nn.Conv2d -> nn.BatchNorm2d):
+ * saves the separate pass over the output that uaps_bn_stats_nhwc makes.  bn_sums: bn_nrep replicas of
+ * [sum[out_c_stride] | sumsq[out_c_stride]] doubles, zeroed by the caller (replicas spread the per-CTA atomics);
+ * hand them to uaps_bn_act_nhwc(sum = bn_sums, sumsq = bn_sums + out_c_stride, ..., nrep = bn_nrep). */
+int uaps_conv_fprop_bn(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
+                       const float* bias, void* out, int out_c_stride, int B, int H, int W,
+                       int cin1, int cin2, int cout, int ks, double* bn_sums, int bn_nrep, cudaStream_t stream);
 /* The same with y = leaky_relu(conv(x) + bias, leaky_slope) in the epilogue (leaky_slope = 1: identity).  With the
  * running statistics of the following BatchNorm2d folded into weights and bias, one call is a whole eval-mode
  * conv -> BN -> LeakyReLU layer of ConvBlock (utilities/UAPS_unet.py:36-43): the validation / inference forward

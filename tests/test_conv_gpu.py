@@ -212,3 +212,33 @@ def test_wgrad_deterministic_split_k(shape):
     base = torch.full_like(a, 0.5)                       # accumulates into what is there
     conv_wgrad(dy, [x], cout, cin, ks, out=base, deterministic=True)
     torch.testing.assert_close(base, a + 0.5, rtol=1e-4, atol=1e-4 * a.abs().max().item() + 1e-6)   # (atomic path: re-association)
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 64, 16, 0, 16, 3), (2, 32, 48, 32, 32, 32, 3), (2, 16, 16, 128, 0, 256, 3), (3, 40, 24, 64, 0, 64, 3),
+                                   (2, 16, 16, 256, 0, 128, 1)])
+def test_conv_epilogue_batchnorm_statistics(shape):
+    """uaps_conv_fprop_bn: the per-channel sum / sum of squares of the conv output, accumulated by the epilogue into
+    replicated fp64 sums, against the statistics of the bf16 output tensor the same call writes."""
+    from uaps_b200.conv import PackedConv
+    B, H, W, c1, c2, co, ks = shape
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(H * W + co)
+    x1 = torch.randn(B, H, W, c1, generator=g, device=dev).to(torch.bfloat16)
+    x2 = torch.randn(B, H, W, c2, generator=g, device=dev).to(torch.bfloat16) if c2 else None
+    w = torch.randn(co, c1 + c2, ks, ks, generator=g, device=dev) * 0.1
+    b = torch.randn(co, generator=g, device=dev)
+    conv = PackedConv(w, b, cin_split=c1 if c2 else None)
+    nrep = 8
+    sums = torch.zeros(nrep * 2 * co, dtype=torch.float64, device=dev)
+    y = conv(x1, x2, bn_sums=sums, bn_nrep=nrep)
+    y_plain = conv(x1, x2)
+    assert torch.equal(y, y_plain)                                   # the statistics do not disturb the output
+    tot = sums.view(nrep, 2, co).sum(0)
+    yf = y.double().view(-1, co)
+    n = yf.shape[0]
+    mean_ref, var_ref = yf.mean(0), yf.var(0, unbiased=False)
+    mean, var = tot[0] / n, tot[1] / n - (tot[0] / n) ** 2
+    # the epilogue sums the fp32 accumulators, the reference the bf16-rounded tensor: unbiased rounding noise of 2^-9 per element
+    assert (mean - mean_ref).abs().max().item() <= 2e-3 * yf.abs().mean().item()
+    assert ((var - var_ref).abs() / var_ref).max().item() <= 2e-3
+    assert (sums.view(nrep, 2, co)[:, 0].abs().sum(1) > 0).sum().item() >= min(nrep, 2)      # the replicas are really used

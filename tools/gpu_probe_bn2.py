@@ -24,7 +24,7 @@ def timeit(fn, n=20):
 mb = npix * C * 2 / 1e6
 for p in (0.0, 0.05):
     t_s = timeit(lambda: lib.uaps_bn_stats_nhwc(y.data_ptr(), npix, C, sums.data_ptr(), sums[C:].data_ptr(), st))
-    t_a = timeit(lambda: lib.uaps_bn_act_nhwc(y.data_ptr(), sums.data_ptr(), sums[C:].data_ptr(), gam.data_ptr(), bet.data_ptr(), None, None, 0.1, 1e-5, 0.01, p, 7, out.data_ptr(), stats.data_ptr(), stats[C:].data_ptr(), npix, C, None, st))
+    t_a = timeit(lambda: lib.uaps_bn_act_nhwc(y.data_ptr(), sums.data_ptr(), sums[C:].data_ptr(), gam.data_ptr(), bet.data_ptr(), None, None, 0.1, 1e-5, 0.01, p, 7, out.data_ptr(), stats.data_ptr(), stats[C:].data_ptr(), npix, C, None, 1, st))
     t_b = timeit(lambda: lib.uaps_bn_act_bwd_nhwc(g.data_ptr(), y.data_ptr(), gam.data_ptr(), bet.data_ptr(), stats.data_ptr(), stats[C:].data_ptr(), 0.01, p, 7, sums2.data_ptr(), sums2[C:].data_ptr(), dy.data_ptr(), None, None, npix, C, None, st))
     print(f"mult {os.environ.get('UAPS_BN_GRID_MULT','1')} p={p}: stats {t_s:6.1f} us ({mb/t_s*1e3/1e3:5.0f} GB/s) | act {t_a:6.1f} us ({2*mb/t_a:5.2f} TB/s) | bwd pair {t_b:6.1f} us ({5*mb/t_b:5.2f} TB/s)")
 x = torch.empty(npix * C, dtype=torch.bfloat16, device=dev)

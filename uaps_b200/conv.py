@@ -99,9 +99,11 @@ class PackedConv:
             self.bias = b.repeat(fold).contiguous()
 
     def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, out_nchw_f32: bool = False,
-                 split: int = 0, slope: float = 1.0):
+                 split: int = 0, slope: float = 1.0, bn_sums: Optional[torch.Tensor] = None, bn_nrep: int = 0):
         """split > 0: return two NHWC tensors holding output channels [0, split) and [split, cout).
-        slope != 1: LeakyReLU(slope) applied to conv + bias in the kernel's epilogue."""
+        slope != 1: LeakyReLU(slope) applied to conv + bias in the kernel's epilogue.
+        bn_sums (fp64, bn_nrep x 2 x pad16(cout), zeroed): the kernel also accumulates the BatchNorm batch statistics of its
+        output there (uaps_conv_fprop_bn)."""
         L.require_cuda(x1)
         assert x1.dtype == torch.bfloat16 and x1.is_contiguous() and x1.dim() == 4
         B, H, W, c1s = x1.shape
@@ -118,6 +120,14 @@ class PackedConv:
             alloc = torch.zeros if (ocs != self.cout and not split and self.fold == 1) else torch.empty
             out = alloc((B, H, W, ocs), dtype=torch.bfloat16, device=x1.device)
         out2 = torch.empty((B, H, W, pad16(self.cout) - split), dtype=torch.bfloat16, device=x1.device) if split else None
+        if bn_sums is not None:
+            assert not out_nchw_f32 and not split and self.fold == 1 and slope == 1.0 and ocs == pad16(self.cout)
+            with L.on_device(x1.device):
+                L.check(L.lib().uaps_conv_fprop_bn(x1.data_ptr(), c1s, None if x2 is None else x2.data_ptr(), c2s,
+                                                   self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(),
+                                                   out.data_ptr(), ocs, B, H, W, self.cin1, self.cin2, self.cout, self.ks,
+                                                   bn_sums.data_ptr(), int(bn_nrep), L.stream_ptr()), "uaps_conv_fprop_bn")
+            return out
         with L.on_device(x1.device):
             L.check(L.lib().uaps_conv_fprop_act(x1.data_ptr(), c1s, None if x2 is None else x2.data_ptr(), c2s,
                                                 self.packed.data_ptr(), None if self.bias is None else self.bias.data_ptr(),
@@ -281,14 +291,14 @@ class _ConvFn(torch.autograd.Function):
     packing; dW by the tcgen05 weight-gradient kernel (conv_wgrad.cu)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, weight, bias, nchw_f32_out, bias_grad):
+    def forward(ctx, x1, x2, weight, bias, nchw_f32_out, bias_grad, bn_sums, bn_nrep):
         co, ci, ks, _ = weight.shape
         c1 = x1.shape[1]
         split = None if x2 is None else c1
         W_img = x1.shape[3]
         cins = [c1] if x2 is None else [c1, x2.shape[1]]
         conv = packed(weight, bias, cin_split=split, fold=pick_fold(cins, co, ks, W_img))
-        y = conv(_nhwc_view(x1), None if x2 is None else _nhwc_view(x2), out_nchw_f32=nchw_f32_out)
+        y = conv(_nhwc_view(x1), None if x2 is None else _nhwc_view(x2), out_nchw_f32=nchw_f32_out, bn_sums=bn_sums, bn_nrep=bn_nrep)
         ctx.save_for_backward(x1, x2, weight)
         ctx.has_bias, ctx.nchw, ctx.bias_grad = bias is not None, nchw_f32_out, bias_grad
         ctx.weight_param = weight
@@ -341,11 +351,12 @@ class _ConvFn(torch.autograd.Function):
                 gb = channel_sums(gy_nhwc, co)
             elif not direct:
                 gb = torch.zeros(co, dtype=torch.float32, device=gy.device)
-        return g1, g2, gw, gb, None, None
+        return g1, g2, gw, gb, None, None, None, None
 
 
 def conv_bf16(x1: torch.Tensor, weight: torch.Tensor, bias, x2: torch.Tensor = None, nchw_f32_out: bool = False,
-              bias_grad: bool = True):
+              bias_grad: bool = True, bn_sums: torch.Tensor = None, bn_nrep: int = 0):
     """bias_grad=False: the conv feeds a train-mode BatchNorm, whose mean subtraction makes d loss / d bias
-    exactly zero -- the reduction is skipped and zeros are returned (the reference accumulates rounding noise)."""
-    return _ConvFn.apply(x1, x2, weight, bias, nchw_f32_out, bias_grad)
+    exactly zero -- the reduction is skipped and zeros are returned (the reference accumulates rounding noise).
+    bn_sums / bn_nrep: also accumulate the batch statistics of the output for that BatchNorm (see PackedConv.__call__)."""
+    return _ConvFn.apply(x1, x2, weight, bias, nchw_f32_out, bias_grad, bn_sums, bn_nrep)

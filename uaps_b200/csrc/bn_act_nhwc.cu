@@ -140,6 +140,7 @@ struct BnParams {
     int G;
     float* dgamma_accum; float* dbeta_accum;      // backward: optional fp32 gradient buffers to accumulate into
     const uint64_t* seed_dev;                     // nullable: per-iteration key added to `seed` (UapsStepState.key_rank)
+    int nrep;                                     // forward: the batch sums arrive as nrep replicas of [sum[C] | sumsq[C]] to be added
 };
 __device__ __forceinline__ uint64_t eff_seed(const BnParams& p) { return p.seed + (p.seed_dev != nullptr ? *p.seed_dev : 0ull); }
 
@@ -151,8 +152,10 @@ __global__ void __launch_bounds__(BT) bn_act_kernel(const uint4* __restrict__ y,
     const int C = 8 * p.G;
     const double n = (double)p.npix;
     for (int c = threadIdx.x; c < C; c += BT) {
-        const double mean = p.sum[c] / n;
-        double var = p.sumsq[c] / n - mean * mean;
+        double s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < p.nrep; ++r) { s1 += p.sum[(size_t)r * 2 * C + c]; s2 += p.sumsq[(size_t)r * 2 * C + c]; }
+        const double mean = s1 / n;
+        double var = s2 / n - mean * mean;
         if (var < 0.0) var = 0.0;
         const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
         s_scale[c] = p.gamma[c] * rstd;
@@ -310,13 +313,14 @@ UAPS_API int uaps_bn_stats_nhwc(const void* y, int64_t npix, int C, double* sum,
 UAPS_API int uaps_bn_act_nhwc(const void* y, const double* sum, const double* sumsq, const float* gamma, const float* beta,
                               float* running_mean, float* running_var, float momentum, float eps, float slope, double p_drop,
                               uint64_t seed, void* out, float* save_mean, float* save_rstd, int64_t npix, int C,
-                              const uint64_t* seed_dev, cudaStream_t stream) {
+                              const uint64_t* seed_dev, int nrep, cudaStream_t stream) {
     if (y == nullptr || sum == nullptr || sumsq == nullptr || gamma == nullptr || beta == nullptr || out == nullptr ||
         save_mean == nullptr || save_rstd == nullptr || npix <= 0)
         return UAPS_EINVAL;
-    if (!valid_c(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
+    if (!valid_c(C) || !(p_drop >= 0.0 && p_drop < 1.0) || nrep < 1 || nrep > 64) return UAPS_ERANGE;
     if (!aligned_to(y, 16) || !aligned_to(out, 16)) return UAPS_EALIGN;
     BnParams p{};
+    p.nrep = nrep;                                // replica r: sum at sum[r * 2C + c], sumsq at sumsq[r * 2C + c]
     p.sum = sum; p.sumsq = sumsq; p.gamma = gamma; p.beta = beta; p.running_mean = running_mean; p.running_var = running_var;
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.momentum = momentum; p.eps = eps; p.slope = slope; p.p = (float)p_drop;
     p.keep_scale = (float)(1.0 / (double)(float)(1.0 - p_drop)); p.seed = seed; p.npix = npix; p.G = C / 8;

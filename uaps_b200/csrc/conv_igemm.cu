@@ -63,7 +63,31 @@ struct ConvArgs {
     int cpp;             // output channels per real pixel in memory (pad16(cout_real))
     int cout_real;
     float act_slope;     // LeakyReLU slope fused into the epilogue (1 = none): inference with BatchNorm folded into the weights
+    // BatchNorm batch statistics of the OUTPUT, accumulated by the epilogue (nullable): bn_nrep replicas of
+    // [sum[cstride] | sumsq[cstride]] fp64, zeroed by the caller; a CTA adds its per-channel partial sums to replica
+    // (blockIdx.x / n_tiles) % bn_nrep -- spreading the same-address atomics, which serialise in L2.
+    double* bn_sums;
+    int bn_nrep, bn_cstride;
 };
+
+// Per-column sums of a 32-lane x 16-column fragment (lane = pixel, v[i] = column i): a recursive-halving butterfly -- at
+// every step a lane keeps half of its columns and sends the other half to its partner -- needs 8+4+2+1+1 = 16 shuffles
+// instead of the 80 of sixteen independent warp reductions.  Afterwards every lane holds the full sum of column
+// (lane >> 1) & 15 (both lanes of a pair hold the same value).
+__device__ __forceinline__ float column_sums16(float (&w)[16], int lane) {
+#define UAPS_HALVE(N, MASK)                                                             \
+    {                                                                                   \
+        const bool up = (lane & MASK) != 0;                                             \
+        _Pragma("unroll") for (int i = 0; i < N; ++i) {                                 \
+            const float send = up ? w[i] : w[i + N];                                    \
+            const float keep = up ? w[i + N] : w[i];                                    \
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);                     \
+        }                                                                               \
+    }
+    UAPS_HALVE(8, 16) UAPS_HALVE(4, 8) UAPS_HALVE(2, 4) UAPS_HALVE(1, 2)
+#undef UAPS_HALVE
+    return w[0] + __shfl_xor_sync(0xffffffffu, w[0], 1);
+}
 
 using namespace uaps::tc;
 
@@ -231,14 +255,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int CK>
-__global__ void __launch_bounds__(THREADS2)
+__global__ void __launch_bounds__(THREADS2, 6)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                              const __grid_constant__ ConvArgs a) {
     constexpr int ROW_BYTES = CK * 2;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2], w_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_stat[4][2][128];          // per epilogue warp: sum | sum of squares of this CTA's output columns
     grid_dep_launch();
+    if (a.bn_sums != nullptr)
+        for (int i = threadIdx.x; i < 4 * 2 * 128; i += THREADS2) (&s_stat[0][0][0])[i] = 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = a.ks - 1;
@@ -403,6 +430,25 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * a.act_slope;
                 }
+                if (a.bn_sums != nullptr) {
+                    // BatchNorm statistics of this layer's output (UAPS_unet.py:37, 42), from the accumulator while it is in
+                    // registers: saves the separate read of the whole output tensor that bn_stats_kernel would do.  The conv
+                    // kernels are bound by the tensor core's operand fetch, not by issue slots, so the ~150 extra instructions
+                    // per 32 x 16 fragment ride in slack.
+                    // (the two quantities one after the other through ONE scratch array: the kernel must stay within 56 registers
+                    // for six resident CTAs per SM)
+                    const float keep = valid ? 1.f : 0.f;
+                    const int col = j * 16 + ((lane >> 1) & 15);
+                    float w[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = v[i] * keep;
+                    const float cs = column_sums16(w, lane);
+                    if ((lane & 1) == 0) s_stat[q][0][col] += cs;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = v[i] * v[i] * keep;
+                    const float cq = column_sums16(w, lane);
+                    if ((lane & 1) == 0) s_stat[q][1][col] += cq;
+                }
                 if (!valid) continue;
                 if (a.out_nchw_f32) {
                     // logits: fp32 NCHW of the REAL image; a folded column block is (sub-pixel, channel)
@@ -452,6 +498,18 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+    if (a.bn_sums != nullptr && blockIdx.x < (unsigned)a.num_tiles) {
+        // this CTA's tiles all have the same output-channel block (the host makes gridDim.x a multiple of n_tiles)
+        const int nt = blockIdx.x % a.n_tiles;
+        double* rep = a.bn_sums + (size_t)((blockIdx.x / a.n_tiles) % a.bn_nrep) * 2 * a.bn_cstride;
+        for (int t = threadIdx.x; t < 2 * a.n_tile; t += THREADS2) {
+            const int which = t / a.n_tile, c = t - which * a.n_tile, gc = nt * a.n_tile + c;
+            if (gc < a.bn_cstride) {
+                const float tot = (s_stat[0][which][c] + s_stat[1][which][c]) + (s_stat[2][which][c] + s_stat[3][which][c]);
+                atomicAdd(rep + (size_t)which * a.bn_cstride + gc, (double)tot);
+            }
+        }
+    }
 }
 
 // ---- weight packing: torch [Cout][Cin][ks][ks] fp32 -> pre-swizzled bf16 stage images -----------------
@@ -690,6 +748,9 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
                                  const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
                                  int cin1, int cin2, int cout, int ks, void* out2, int out2_c_stride, int split,
                                  int fold, float leaky_slope, cudaStream_t stream);
+UAPS_API int uaps_conv_fprop_bn(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
+                                const float* bias, void* out, int out_c_stride, int B, int H, int W, int cin1, int cin2,
+                                int cout, int ks, double* bn_sums, int bn_nrep, cudaStream_t stream);
 
 UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
                              const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
@@ -701,10 +762,37 @@ UAPS_API int uaps_conv_fprop(const void* x1, int c1_stride, const void* x2, int 
 
 // Same with y = leaky_relu(conv(x) + bias, leaky_slope) applied in the epilogue (leaky_slope = 1: identity).  With BatchNorm's
 // running statistics folded into the weights and bias this is a whole eval-mode ConvBlock layer (UAPS_unet.py:36-43) in one kernel.
+namespace {
+int conv_fprop_impl(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed, const float* bias,
+                    void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W, int cin1, int cin2, int cout, int ks,
+                    void* out2, int out2_c_stride, int split, int fold, float leaky_slope, double* bn_sums, int bn_nrep,
+                    cudaStream_t stream);
+}
+
 UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
                                  const float* bias, void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W,
                                  int cin1, int cin2, int cout, int ks, void* out2, int out2_c_stride, int split,
                                  int fold, float leaky_slope, cudaStream_t stream) {
+    return conv_fprop_impl(x1, c1_stride, x2, c2_stride, w_packed, bias, out, out_c_stride, out_nchw_f32, B, H, W, cin1, cin2, cout,
+                           ks, out2, out2_c_stride, split, fold, leaky_slope, nullptr, 0, stream);
+}
+
+// conv + bias -> bf16 NHWC as uaps_conv_fprop, and the BatchNorm batch statistics of that output in the same kernel:
+// bn_sums = bn_nrep replicas of [sum[out_c_stride] | sumsq[out_c_stride]] doubles, zeroed by the caller; the statistics of the
+// whole output are the sums over the replicas (uaps_bn_act_nhwc takes them as they are).
+UAPS_API int uaps_conv_fprop_bn(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed,
+                                const float* bias, void* out, int out_c_stride, int B, int H, int W, int cin1, int cin2,
+                                int cout, int ks, double* bn_sums, int bn_nrep, cudaStream_t stream) {
+    if (bn_sums == nullptr || bn_nrep < 1 || bn_nrep > 64 || !aligned_to(bn_sums, 8)) return UAPS_EINVAL;
+    return conv_fprop_impl(x1, c1_stride, x2, c2_stride, w_packed, bias, out, out_c_stride, 0, B, H, W, cin1, cin2, cout, ks, nullptr,
+                           0, 0, 1, 1.0f, bn_sums, bn_nrep, stream);
+}
+
+namespace {
+int conv_fprop_impl(const void* x1, int c1_stride, const void* x2, int c2_stride, const void* w_packed, const float* bias,
+                    void* out, int out_c_stride, int out_nchw_f32, int B, int H, int W, int cin1, int cin2, int cout, int ks,
+                    void* out2, int out2_c_stride, int split, int fold, float leaky_slope, double* bn_sums, int bn_nrep,
+                    cudaStream_t stream) {
     // fold = F > 1: run the virtual convolution on the [B, H, W/F, F*C] views of the same tensors.  Requires the
     // tensors' channel pitch to equal their padded channel count (so F pixels are contiguous) and W % F == 0.
     Plan pl;
@@ -738,6 +826,8 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
     a.out2 = out2; a.split = split; a.out2_stride = out2_c_stride;
     a.fold = fold; a.cpp = (fold > 1 || out2 != nullptr) ? cpp : cout; a.cout_real = cout_real;
     a.act_slope = leaky_slope;
+    a.bn_sums = bn_sums; a.bn_nrep = bn_nrep; a.bn_cstride = out_c_stride;
+    if (bn_sums != nullptr && (getenv("UAPS_CONV_V1") != nullptr || out_nchw_f32 || out2 != nullptr || fold != 1)) return UAPS_EINVAL;
     if (leaky_slope != 1.0f && getenv("UAPS_CONV_V1") != nullptr) return UAPS_EINVAL;      // the v1 kernel has no activation epilogue
     if (out2 != nullptr && (out_nchw_f32 || (split % 16) != 0 || split <= 0 || split >= cpp || (out2_c_stride % 8) != 0 ||
                             !aligned_to(out2, 16) || getenv("UAPS_CONV_V1") != nullptr))
@@ -787,7 +877,7 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
         const size_t smem = (size_t)w_region + (size_t)stages * stage_bytes + 1024;
         int tmem_cols = 32;
         while (tmem_cols < 2 * pl.n_tile) tmem_cols <<= 1;
-        int per_sm = (int)((227 * 1024) / (smem + 2048));
+        int per_sm = (int)((227 * 1024) / (smem + 2048 + 4096));      // + static shared memory (barriers, BN-statistics scratch)
         if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
         // measured on B200 (16-channel layers, B=64): 4 CTAs/SM 88 us, 6 -> 80 us, 8 -> 99 us
         static const int cap_env = [] { const char* e = getenv("UAPS_CONV_CTAS_PER_SM"); return e ? atoi(e) : 6; }();
@@ -795,6 +885,10 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
         if (per_sm < 1) per_sm = 1;
         long long gridx = (long long)device_info().sm_count * per_sm;
         if (gridx > a.num_tiles) gridx = a.num_tiles;
+        if (bn_sums != nullptr && pl.n_tiles > 1) {          // every CTA must see ONE output-channel block (its statistics columns)
+            gridx = gridx / pl.n_tiles * pl.n_tiles;
+            if (gridx < pl.n_tiles) gridx = pl.n_tiles;
+        }
 #define UAPS_CONV_LAUNCH2(CKV)                                                                                             \
         e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<CKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         if (e != cudaSuccess) return (int)e;                                                                                   \
@@ -805,3 +899,4 @@ UAPS_API int uaps_conv_fprop_act(const void* x1, int c1_stride, const void* x2, 
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
+}  // namespace

@@ -62,7 +62,7 @@ class DeviceStepState:
 
 
 class StepContext:
-    def __init__(self, device, arena_doubles: int = 1 << 17, state: "DeviceStepState" = None, xchg=None, packer=None):
+    def __init__(self, device, arena_doubles: int = 1 << 18, state: "DeviceStepState" = None, xchg=None, packer=None):
         self.device = device
         self.arena = torch.zeros(arena_doubles, dtype=torch.float64, device=device)
         self.used = 0

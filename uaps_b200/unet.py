@@ -32,6 +32,7 @@ from .resample import maxpool2, upsample2x
 FT_CHNS = (16, 32, 64, 128, 256)            # UAPS_unet.py:212
 ENC_DROPOUT = (0.05, 0.1, 0.2, 0.3, 0.5)    # :214
 _AUX_KINDS = ("noise", "dropout", "fdrop")  # :227, :229, :231; a 4th/5th aux decoder re-uses them in order
+BN_NREP = 8                                 # replicas of the BatchNorm sums a conv epilogue accumulates into (spreads the atomics)
 
 
 def _holder(**children: nn.Module) -> nn.Module:
@@ -118,17 +119,29 @@ class UNet_UAPS(nn.Module):
         return dec.out_conv(x)
 
     # ---- bf16 / tcgen05 path ------------------------------------------------------------------
+    @staticmethod
+    def _bn_sums(cout: int, device) -> torch.Tensor:
+        """Zeroed fp64 [BN_NREP][sum | sumsq][pad16(cout)] for the conv epilogue's BatchNorm statistics."""
+        from . import stepctx
+        n = BN_NREP * 2 * pad16(cout)
+        sc = stepctx.current()
+        return sc.take(n) if sc is not None else torch.zeros(n, dtype=torch.float64, device=device)
+
     def _block16(self, x, blk, p_drop, keep, x2=None):
         cc = blk.conv_conv
         c0, b0, c4, b4 = (cc.get_submodule(n) for n in ("0", "1", "4", "5"))
         # a conv bias in front of a BatchNorm that uses BATCH statistics has an analytically zero gradient; with running
         # statistics (eval mode, e.g. fine-tuning with frozen BN) it does not
         bg = not self.training
-        y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=bg)
         if self.training and keep is None:
-            # fused BN(batch stats) + LeakyReLU + Philox dropout: 2 kernels forward, 2 backward
-            y = bn_lrelu_dropout(y, b0, p_drop)
-            return bn_lrelu_dropout(conv_bf16(y, c4.weight, c4.bias, bias_grad=bg), b4, 0.0)
+            # conv (its epilogue also accumulates the BatchNorm batch statistics) -> fused BN(batch stats) + LeakyReLU +
+            # Philox dropout: 2 kernels per layer forward, 2 + dgrad + wgrad backward
+            s0, s4 = self._bn_sums(c0.weight.shape[0], x.device), self._bn_sums(c4.weight.shape[0], x.device)
+            y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=bg, bn_sums=s0, bn_nrep=BN_NREP)
+            y = bn_lrelu_dropout(y, b0, p_drop, sums=s0, nrep=BN_NREP)
+            y = conv_bf16(y, c4.weight, c4.bias, bias_grad=bg, bn_sums=s4, bn_nrep=BN_NREP)
+            return bn_lrelu_dropout(y, b4, 0.0, sums=s4, nrep=BN_NREP)
+        y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=bg)
         y = F.leaky_relu(b0(y), 0.01)                         # eval mode / injected dropout mask (parity runs)
         if p_drop > 0.0 and self.training:
             y = y * (keep.to(y.dtype) * (1.0 / (1.0 - p_drop)))
