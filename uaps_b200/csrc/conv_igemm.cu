@@ -262,10 +262,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2], w_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_stat[4][2][128];          // per epilogue warp: sum | sum of squares of this CTA's output columns
     grid_dep_launch();
-    if (a.bn_sums != nullptr)
-        for (int i = threadIdx.x; i < 4 * 2 * 128; i += THREADS2) (&s_stat[0][0][0])[i] = 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = a.ks - 1;
@@ -278,6 +275,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
     const int w_region = a.resident ? ((w_total + 1023) & ~1023) : 0;
     const int stage_bytes = (a_bytes + (a.resident ? 0 : b_bytes) + 1023) & ~1023;
     unsigned char* stage0 = smem + w_region;
+    // BatchNorm-statistics scratch [epilogue warp][sum | sumsq][n_tile] floats, behind the stages (only when requested)
+    float* s_stat = reinterpret_cast<float*>(stage0 + (size_t)a.stages * stage_bytes);
+    if (a.bn_sums != nullptr)
+        for (int i = threadIdx.x; i < 4 * 2 * a.n_tile; i += THREADS2) s_stat[i] = 0.f;
 
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * a.n_tile) tmem_cols <<= 1;
@@ -443,11 +444,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
 #pragma unroll
                     for (int i = 0; i < 16; ++i) w[i] = v[i] * keep;
                     const float cs = column_sums16(w, lane);
-                    if ((lane & 1) == 0) s_stat[q][0][col] += cs;
+                    if ((lane & 1) == 0) s_stat[(q * 2 + 0) * a.n_tile + col] += cs;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) w[i] = v[i] * v[i] * keep;
                     const float cq = column_sums16(w, lane);
-                    if ((lane & 1) == 0) s_stat[q][1][col] += cq;
+                    if ((lane & 1) == 0) s_stat[(q * 2 + 1) * a.n_tile + col] += cq;
                 }
                 if (!valid) continue;
                 if (a.out_nchw_f32) {
@@ -505,7 +506,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
         for (int t = threadIdx.x; t < 2 * a.n_tile; t += THREADS2) {
             const int which = t / a.n_tile, c = t - which * a.n_tile, gc = nt * a.n_tile + c;
             if (gc < a.bn_cstride) {
-                const float tot = (s_stat[0][which][c] + s_stat[1][which][c]) + (s_stat[2][which][c] + s_stat[3][which][c]);
+                const float tot = (s_stat[(0 + which) * a.n_tile + c] + s_stat[(2 + which) * a.n_tile + c]) +
+                                  (s_stat[(4 + which) * a.n_tile + c] + s_stat[(6 + which) * a.n_tile + c]);
                 atomicAdd(rep + (size_t)which * a.bn_cstride + gc, (double)tot);
             }
         }
@@ -874,10 +876,11 @@ int conv_fprop_impl(const void* x1, int c1_stride, const void* x2, int c2_stride
         if ((size_t)w_region + (size_t)stages * stage_bytes > 220 * 1024) stages = 2;
         while (stages > 1 && (size_t)w_region + (size_t)stages * stage_bytes > 220 * 1024) --stages;
         a.stages = stages;
-        const size_t smem = (size_t)w_region + (size_t)stages * stage_bytes + 1024;
+        const size_t stat_bytes = bn_sums != nullptr ? (size_t)4 * 2 * pl.n_tile * sizeof(float) : 0;   // BN-statistics scratch
+        const size_t smem = (size_t)w_region + (size_t)stages * stage_bytes + stat_bytes + 1024;
         int tmem_cols = 32;
         while (tmem_cols < 2 * pl.n_tile) tmem_cols <<= 1;
-        int per_sm = (int)((227 * 1024) / (smem + 2048 + 4096));      // + static shared memory (barriers, BN-statistics scratch)
+        int per_sm = (int)((227 * 1024) / (smem + 2048));
         if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
         // measured on B200 (16-channel layers, B=64): 4 CTAs/SM 88 us, 6 -> 80 us, 8 -> 99 us
         static const int cap_env = [] { const char* e = getenv("UAPS_CONV_CTAS_PER_SM"); return e ? atoi(e) : 6; }();

@@ -33,6 +33,7 @@ FT_CHNS = (16, 32, 64, 128, 256)            # UAPS_unet.py:212
 ENC_DROPOUT = (0.05, 0.1, 0.2, 0.3, 0.5)    # :214
 _AUX_KINDS = ("noise", "dropout", "fdrop")  # :227, :229, :231; a 4th/5th aux decoder re-uses them in order
 BN_NREP = 8                                 # replicas of the BatchNorm sums a conv epilogue accumulates into (spreads the atomics)
+BN_FUSE_MAX_COUT = int(__import__("os").environ.get("UAPS_BN_FUSE_MAX_COUT", "32"))   # widest layer whose conv epilogue takes the statistics
 
 
 def _holder(**children: nn.Module) -> nn.Module:
@@ -136,11 +137,18 @@ class UNet_UAPS(nn.Module):
         if self.training and keep is None:
             # conv (its epilogue also accumulates the BatchNorm batch statistics) -> fused BN(batch stats) + LeakyReLU +
             # Philox dropout: 2 kernels per layer forward, 2 + dgrad + wgrad backward
-            s0, s4 = self._bn_sums(c0.weight.shape[0], x.device), self._bn_sums(c4.weight.shape[0], x.device)
-            y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=bg, bn_sums=s0, bn_nrep=BN_NREP)
-            y = bn_lrelu_dropout(y, b0, p_drop, sums=s0, nrep=BN_NREP)
-            y = conv_bf16(y, c4.weight, c4.bias, bias_grad=bg, bn_sums=s4, bn_nrep=BN_NREP)
-            return bn_lrelu_dropout(y, b4, 0.0, sums=s4, nrep=BN_NREP)
+            # The epilogue statistics cost the conv ~150 instructions per 32 x 16 accumulator fragment.  Measured (B = 64): for the
+            # 16/32-channel layers that is +5..18 us on the conv against 16..29 us for the separate statistics pass it replaces;
+            # for 64+ channels (8 fragments per tile, small tensors) it costs more than the 8 us pass -> those keep bn_stats.
+            cout = c0.weight.shape[0]
+            if cout <= BN_FUSE_MAX_COUT:
+                s0, s4 = self._bn_sums(cout, x.device), self._bn_sums(cout, x.device)
+                y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=bg, bn_sums=s0, bn_nrep=BN_NREP)
+                y = bn_lrelu_dropout(y, b0, p_drop, sums=s0, nrep=BN_NREP)
+                y = conv_bf16(y, c4.weight, c4.bias, bias_grad=bg, bn_sums=s4, bn_nrep=BN_NREP)
+                return bn_lrelu_dropout(y, b4, 0.0, sums=s4, nrep=BN_NREP)
+            y = bn_lrelu_dropout(conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=bg), b0, p_drop)
+            return bn_lrelu_dropout(conv_bf16(y, c4.weight, c4.bias, bias_grad=bg), b4, 0.0)
         y = conv_bf16(x, c0.weight, c0.bias, x2=x2, bias_grad=bg)
         y = F.leaky_relu(b0(y), 0.01)                         # eval mode / injected dropout mask (parity runs)
         if p_drop > 0.0 and self.training:
