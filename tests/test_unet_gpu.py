@@ -90,13 +90,20 @@ def test_net_factory_and_input_check():
     assert len(out) == 4 and out[0].shape == (2, 2, 64, 96)
 
 
-def _torch_bf16_conv(x1, weight, bias, x2=None, nchw_f32_out=False, bias_grad=True):
-    """Test-side stand-in for uaps_b200.conv.conv_bf16: the same bf16 operands through cuDNN."""
+def _torch_bf16_conv(x1, weight, bias, x2=None, nchw_f32_out=False, bias_grad=True, bn_sums=None, bn_nrep=0):
+    """Test-side stand-in for uaps_b200.conv.conv_bf16: the same bf16 operands through cuDNN (and, like the real conv's
+    epilogue, the BatchNorm batch sums of the output when asked for)."""
     import torch.nn.functional as F
     xin = x1 if x2 is None else torch.cat([x1, x2], dim=1)
     ci = weight.shape[1]
     y = F.conv2d(xin[:, :ci], weight.to(torch.bfloat16), None if bias is None else bias.to(torch.bfloat16),
                  padding=weight.shape[-1] // 2)
+    if bn_sums is not None:
+        with torch.no_grad():
+            yd = y.detach().double()
+            v = bn_sums.view(bn_nrep, 2, -1)
+            v[0, 0] += yd.sum(dim=(0, 2, 3))
+            v[0, 1] += (yd * yd).sum(dim=(0, 2, 3))
     return y.float().contiguous() if nchw_f32_out else y.contiguous(memory_format=torch.channels_last)
 
 
