@@ -47,7 +47,7 @@ int pick_vec(const float* const* z, float* const* o, int K, int64_t HW) {
 // Kernel variant for a call: pass 1 runs 4 pixels/thread, pass 2 two (both software-pipelined) when
 // the planes are 16-byte aligned (HW % 4 == 0); odd shapes take the scalar kernels and UAPS_LOSS_EXACT
 // the torch-order ones.  UAPS_LOSS_IMPL=<0..2> overrides the choice (tuning knob, not part of the ABI).
-int pick_impl(int avail_vec, int flags, bool pass2) {
+int pick_impl(int avail_vec, int flags, bool pass2, int kc) {
     static const int forced = [] { const char* e = getenv("UAPS_LOSS_IMPL"); return e ? atoi(e) : -1; }();
     static const int forced_p1 = [] { const char* e = getenv("UAPS_LOSS_P1_IMPL"); return e ? atoi(e) : -1; }();   // pass 1 only
     if (flags & UAPS_LOSS_EXACT) return IMPL_EXACT;
@@ -57,7 +57,12 @@ int pick_impl(int avail_vec, int flags, bool pass2) {
         return forced_p1;
     if (forced >= 0 && forced <= IMPL_SCALAR) return forced;
     if (avail_vec < 4) return IMPL_VEC2_PF;
-    return pass2 ? IMPL_VEC2_PF : IMPL_VEC4_PF;
+    // pass 2: two pixels per thread at K*C = 16 (registers), four when there are few class planes (C = 2 data sets): with
+    // K*C <= 12 the 4-pixel kernel keeps as many loads in flight as the 2-pixel one does at K*C = 16 -- measured on B200:
+    // K=4 C=2 32x512x512 pass 2 106.8 -> 96.3 us (0.77 -> 0.85 of HBM peak), K=5 C=2 32x240x640 79.4 -> 75.4 us, K=3 C=4 32x1024x1024 fwd+bwd 0.736 -> 0.783
+    static const int p2_vec4_max_kc = [] { const char* e = getenv("UAPS_LOSS_P2_VEC4_MAXKC"); return e ? atoi(e) : 12; }();
+    if (pass2) return kc <= p2_vec4_max_kc ? IMPL_VEC4_PF : IMPL_VEC2_PF;
+    return IMPL_VEC4_PF;
 }
 
 int dispatch_k(int K, int C, int impl, bool sup, bool pass2, const LossArgs& a, float* partials, const float* sc,
@@ -215,7 +220,7 @@ static int loss_pass1_impl(const float* const* z, int K, int B, int C, int64_t H
     }
     a.labels = labels; a.pseudo = pseudo_out; a.HW = HW; a.B = B; a.w_dev = labels == nullptr ? wcw_dev : nullptr;
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + WS_HEADER_BYTES);
-    const int impl = pick_impl(pick_vec(z, exp_var_out, K, HW), flags, false);
+    const int impl = pick_impl(pick_vec(z, exp_var_out, K, HW), flags, false, K * C);
     int nblocks = 0;
     rc = dispatch_k(K, C, impl, labels != nullptr, false, a, partials, nullptr, nullptr, &nblocks, stream);
     if (rc != UAPS_OK) return rc;
@@ -342,7 +347,7 @@ UAPS_API int uaps_loss_pass2(const float* const* z, int K, int B, int C, int64_t
         a.out[k] = dz[k];
     }
     a.labels = labels; a.pseudo = nullptr; a.HW = HW; a.B = B; a.w_dev = labels == nullptr ? wcw_dev : nullptr;
-    const int impl = pick_impl(pick_vec(z, dz, K, HW), flags, true);
+    const int impl = pick_impl(pick_vec(z, dz, K, HW), flags, true, K * C);
     int nblocks = 0;
     return dispatch_k(K, C, impl, labels != nullptr, true, a, nullptr, scalars, grad_out, &nblocks, stream);
 }
