@@ -350,7 +350,7 @@ def loss_roofline(c, ms_total, t1, t2, steps, world, peak, peak_src):
     ms_step = ms_total / steps
     bytes1, bytes2 = 4 * K * C * N, 8 * K * C * N
     ach1, ach2 = bytes1 / (t1 * 1e-3) / 1e9, bytes2 / (t2 * 1e-3) / 1e9
-    vec = "VEC=2" if K * C <= 24 else "VEC=1"
+    vec = "VEC=4" if K * C <= 12 else ("VEC=2" if K * C <= 24 else "VEC=1")     # fused_loss.cu:pick_impl / dispatch
     roof = {"bound": "hbm", "kernel": f"loss_pass2_kernel<K={K},C={C},{vec},PF> (uaps_loss_pass2)", "achieved": ach2, "peak": peak,
             "unit": "GB/s", "frac": ach2 / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes2,
             "fwd_bwd_frac": (bytes1 + bytes2) / (ms_step * 1e-3) / 1e9 / peak}
