@@ -242,3 +242,74 @@ def test_conv_epilogue_batchnorm_statistics(shape):
     assert (mean - mean_ref).abs().max().item() <= 2e-3 * yf.abs().mean().item()
     assert ((var - var_ref).abs() / var_ref).max().item() <= 2e-3
     assert (sums.view(nrep, 2, co)[:, 0].abs().sum(1) > 0).sum().item() >= min(nrep, 2)      # the replicas are really used
+
+
+# conv_sn_kernel (3x3 layers with <= 64 output channels and input channels >= 2 x output channels or >= 64: the horizontal
+# taps sit in the MMA's N dimension, the pixel shift is done by the epilogue, and the shifts that cross a 32-pixel tile edge
+# are carried from tile to tile along a 4-row band): widths with several tiles per band, a ragged last tile, a last tile that
+# ends exactly on lane 31, ragged bands, every epilogue variant, every channel-chunk width and epilogue-warp count.
+SN_SHAPES = [
+    (2, 10, 100, 32, 16),      # 4 tiles per band (100 = 3 x 32 + 4), H = 10: a 2-row last band
+    (1, 7, 96, 64, 32),        # exactly 3 tiles: the band's last pixel is lane 31 of the last tile
+    (2, 9, 33, 96, 48),        # one pixel in the second tile; n_co = 48 -> N = 144, three chunks of 32
+    (1, 12, 160, 64, 64),
+    (1, 5, 72, 128, 64),       # two channel chunks of 64 (data gradient of down3's first conv)
+    (2, 8, 64, 48, 16),        # three chunks of 16
+    (1, 6, 40, 64, 4),         # 4 real output channels in a 16-column group
+    (1, 4, 31, 80, 48),        # five chunks of 16; a single ragged tile
+]
+
+
+@pytest.mark.parametrize("B,H,W,ci,co", SN_SHAPES)
+def test_sn_kernel_tile_edges(B, H, W, ci, co):
+    from uaps_b200.conv import PackedConv, from_nhwc, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(H * 131 + W + ci + 3 * co)
+    x = torch.randn(B, ci, H, W, generator=g).to(dev)
+    w = (torch.randn(co, ci, 3, 3, generator=g) * (2.0 / (ci * 9)) ** 0.5).to(dev)
+    b = torch.randn(co, generator=g).to(dev)
+    ref = _ref(x, w, b, 3)
+    scale = ref.abs().max().item()
+    conv = PackedConv(w, b)
+    xn = to_nhwc_bf16(x)
+    out = from_nhwc(conv(xn), co)
+    err = (out - ref).abs()
+    assert err.max().item() <= 1e-2 * scale, (err.max().item(), scale, torch.nonzero(err > 1e-2 * scale)[:8].tolist())
+    # LeakyReLU epilogue (inference with BatchNorm folded in)
+    out = from_nhwc(conv(xn, slope=0.01), co)
+    assert (out - F.leaky_relu(ref, 0.01)).abs().max().item() <= 1e-2 * scale
+    # fp32 NCHW epilogue (logits)
+    out = conv(xn, out_nchw_f32=True)
+    assert (out - ref).abs().max().item() <= 2e-3 * scale
+    # BatchNorm statistics epilogue: same output, sums of exactly the pixels of the image
+    sums = torch.zeros(4 * 2 * ((co + 15) // 16 * 16), dtype=torch.float64, device=dev)
+    y = conv(xn, bn_sums=sums, bn_nrep=4)
+    assert torch.equal(y, conv(xn))
+    cp = (co + 15) // 16 * 16
+    tot = sums.view(4, 2, cp).sum(0)[:, :co]
+    yf = y[..., :co].double().reshape(-1, co)
+    assert (tot[0] - yf.sum(0)).abs().max().item() <= 3e-3 * yf.abs().sum(0).max().item()
+    assert ((tot[1] - (yf * yf).sum(0)).abs() / (yf * yf).sum(0)).max().item() <= 3e-3
+
+
+def test_sn_kernel_concat_and_split_over_several_tiles():
+    from uaps_b200.conv import PackedConv, from_nhwc, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(77)
+    for c, H, W in ((16, 9, 100), (32, 6, 70), (64, 5, 64)):
+        skip, up = torch.randn(2, c, H, W, generator=g).to(dev), torch.randn(2, c, H, W, generator=g).to(dev)
+        w = (torch.randn(c, 2 * c, 3, 3, generator=g) * (1.0 / (18 * c)) ** 0.5).to(dev)
+        b = torch.randn(c, generator=g).to(dev)
+        ref = _ref(torch.cat([skip, up], 1), w, b, 3)
+        out = from_nhwc(PackedConv(w, b, cin_split=c)(to_nhwc_bf16(skip), to_nhwc_bf16(up)), c)
+        assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item(), c
+    for c, co, H, W in ((16, 64, 9, 100), (32, 128, 6, 70)):  # data gradient of a concat conv, written into two tensors
+        w = (torch.randn(co, 2 * c, 3, 3, generator=g) * 0.05).to(dev)
+        dy = torch.randn(2, co, H, W, generator=g).to(dev)
+        x = torch.zeros(2, 2 * c, H, W, device=dev, requires_grad=True)
+        F.conv2d(x, w.bfloat16().float(), padding=1).backward(dy.bfloat16().float())
+        conv = PackedConv(w, None, transpose=True)
+        whole = conv(to_nhwc_bf16(dy))
+        a, b2 = conv(to_nhwc_bf16(dy), split=c)
+        assert torch.equal(a, whole[..., :c]) and torch.equal(b2, whole[..., c:])
+        assert (from_nhwc(whole, 2 * c) - x.grad).abs().max().item() <= 1e-2 * x.grad.abs().max().item()

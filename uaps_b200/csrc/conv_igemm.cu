@@ -29,6 +29,7 @@
 // [-> LeakyReLU] -> bf16 NHWC / fp32 NCHW), so tile i's epilogue overlaps tile i+1's MMAs.  Layers whose packed weights fit
 // 80 KB keep them resident in shared memory and load ONE x-halo activation box per channel chunk for all nine taps.
 // conv_igemm_kernel (UAPS_CONV_V1=1): the first, one-tile-per-CTA version, kept for A/B profiling.
+#include <cstdio>
 #include <cstdlib>
 #include "tc_common.cuh"
 
@@ -514,6 +515,302 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
     }
 }
 
+// ---- v3 ("SN"): the horizontal taps in the N dimension ----------------------------------------------------------
+// The kernels above are bound by the tensor core's shared-memory operand fetch: every tcgen05.mma re-reads its 128-row A
+// operand, (128 + N) * 32 bytes at 64 B/clk, so a 3x3 conv with N = 16 output channels spends 9 x 72 clocks per 128-pixel
+// tile on 9 x 4 clocks of arithmetic.  This kernel fetches each A tile three times instead of nine:
+//
+//     Y_s[p, co] = sum_{r, ci} W[co, ci, r, s] * in[p + (r - 1) rows, ci]         for all three s in ONE MMA:
+//                  M = 128 pixels, K = (r, ci), N = (s, co) = 3 * n_co
+//     out[p, co] = Y_0[p - 1, co] + Y_1[p, co] + Y_2[p + 1, co]                    in the epilogue
+//
+// so a tile costs 3 * CK/16 MMAs per channel chunk at (128 + 3 n_co) / 2 clocks each: 264 clocks instead of 648 for
+// 16 -> 16 channels, 1920 instead of 3456 for 64 -> 64.  The pixel shift is a warp shuffle: a tile is 4 image rows x 32
+// pixels, an epilogue warp owns one row (TMEM lanes 32q..32q+31 = 32 consecutive x) and 16 output channels, and it
+// finishes the pixels ONE TO THE LEFT of its lanes: lane l of tile t writes pixel x = 32 t + l - 1 =
+// Y_0[lane l - 2] + Y_1[lane l - 1] + Y_2[lane l], two rotating shuffles whose wrapped-around values (lanes 30 / 31 of this
+// tile) are exactly what lanes 0 / 1 of the NEXT tile of the band need -- they stay in registers from tile to tile.  A CTA
+// sweeps a 4-row band left to right; nothing is computed twice, every output is written once, no pixel waits for data of
+// a later tile.  (When W is a multiple of 32 the band's last pixel is finished by lane 31 of the last tile.)
+//
+//   A operand.  One TMA box {CK, 32 x, 4 + 2 y} per channel chunk: rows (y, x), row pitch = swizzle span; vertical tap r is
+//   the same tile read 32 rows further down (atom-aligned).  Rows / columns outside the image are zero-filled.
+//   B operand.  All weights resident in shared memory: block (chunk, r) = [3 * n_co rows (s, co)][CK], pre-swizzled.
+//   D.  Two accumulators of 3 * n_co fp32 columns.
+//   Warps.  0 = TMA producer, 1 = MMA issuer, 2 .. 2 + 4 NG - 1 = epilogue: warp w drains TMEM lane quarter w % 4 (image
+//   row w % 4 of the band) of channel group (w - 2) / 4.  The epilogue is ~170 instructions per 32 x 16 fragment and a lone
+//   warp issues one every ~9 clocks (ncu), so the 64-channel layers need all sixteen of them to stay under the MMA time.
+//   Stores are one contiguous 32 * 32 bytes per warp (NHWC) or 128 bytes per class plane (NCHW logits).
+constexpr int SN_TILE_H = 4, SN_TILE_W = 32;
+
+// NG = n_co / 16 output-channel groups = epilogue warps per TMEM lane quarter.  (Fragments of 8 columns -- twice the warps --
+// were measured too: 16 -> 16 channels 89 us against 85 us, the epilogue is bound by issue slots, not by latency.)
+template <int NG> struct SnCfg {
+    static constexpr int EPI_WARPS = 4 * NG;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    // co-resident CTAs: at most 512 / (2 * 48 NG rounded up to a power of two) by their TMEM columns
+    static constexpr int MIN_CTAS = NG == 1 ? 4 : (NG == 2 ? 2 : 1);
+};
+
+template <int CK, int NG>
+__global__ void __launch_bounds__((SnCfg<NG>::THREADS), (SnCfg<NG>::MIN_CTAS))
+conv_sn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+               const __grid_constant__ ConvArgs a) {
+    constexpr int ROW_BYTES = CK * 2;
+    constexpr int A_BYTES = (SN_TILE_H + 2) * SN_TILE_W * ROW_BYTES;          // 6 / 12 / 24 KB, a multiple of 1024
+    constexpr int NCO = 16 * NG, N3 = 3 * NCO;
+    constexpr int CW = 16;                                                     // columns per epilogue warp
+    constexpr int NTHREADS = SnCfg<NG>::THREADS, EPI_WARPS = SnCfg<NG>::EPI_WARPS;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2], w_bar;
+    __shared__ uint32_t tmem_base_smem;
+    grid_dep_launch();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = a.chunks[0] + (a.nseg > 1 ? a.chunks[1] : 0);
+    constexpr int RBLOCK = N3 * ROW_BYTES;                                     // weights of one (chunk, r)
+    const int w_total = chunks * 3 * RBLOCK;
+    const int w_region = (w_total + 1023) & ~1023;
+    unsigned char* stage0 = smem + w_region;
+    float* s_carry = reinterpret_cast<float*>(stage0 + (size_t)a.stages * A_BYTES);   // [epilogue warp][4][CW]
+    float* s_bias = s_carry + EPI_WARPS * 4 * CW;                                      // [n_co]
+    float* s_stat = s_bias + NCO;                                                      // [lane quarter][sum | sumsq][n_co]
+    for (int i = threadIdx.x; i < NCO; i += NTHREADS) s_bias[i] = (a.bias != nullptr && i < a.cout) ? a.bias[i] : 0.f;
+    if (a.bn_sums != nullptr)
+        for (int i = threadIdx.x; i < 4 * 2 * NCO; i += NTHREADS) s_stat[i] = 0.f;
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * N3) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, EPI_WARPS); }
+        mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+    grid_dep_wait();
+
+    // work unit = (image, band of 4 rows), swept left to right; a.num_tiles = number of units, a.tiles_y = bands per image
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer ----------------------------------------------------------------------
+            mbar_expect_tx(&w_bar, w_total);
+            for (int off = 0; off < w_total; off += 16384)
+                bulk_g2s(smem + off, a.w_packed + off, min(16384, w_total - off), &w_bar);
+            int itg = 0;
+            for (int unit = blockIdx.x; unit < a.num_tiles; unit += gridDim.x) {
+                const int n_img = unit / a.tiles_y, y0 = (unit - n_img * a.tiles_y) * SN_TILE_H;
+                for (int tx = 0; tx < a.tiles_x; ++tx) {
+                    for (int seg = 0; seg < a.nseg; ++seg) {
+                        const CUtensorMap* map = seg == 0 ? &map0 : &map1;
+                        for (int ch = 0; ch < a.chunks[seg]; ++ch, ++itg) {
+                            const int st = itg % a.stages;
+                            mbar_wait_relaxed(empty_bar + st, ((itg / a.stages) & 1) ^ 1);
+                            mbar_expect_tx(full_bar + st, A_BYTES);
+                            tma_load_4d(stage0 + (size_t)st * A_BYTES, map, ch * CK, tx * SN_TILE_W, y0 - 1, n_img, full_bar + st);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ------------------------------------------------------------------------
+            const uint32_t idesc = make_idesc(N3);
+            const uint32_t wbase = smem_u32(smem);
+            mbar_wait(&w_bar, 0);
+            int itg = 0, tcount = 0;
+            for (int unit = blockIdx.x; unit < a.num_tiles; unit += gridDim.x) {
+                for (int tx = 0; tx < a.tiles_x; ++tx, ++tcount) {
+                    const int buf = tcount & 1;
+                    mbar_wait(acc_empty + buf, ((tcount >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d = tmem_d + (uint32_t)(buf * N3);
+                    for (int c = 0; c < chunks; ++c, ++itg) {
+                        const int st = itg % a.stages;
+                        mbar_wait(full_bar + st, (itg / a.stages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = smem_u32(stage0 + (size_t)st * A_BYTES);
+                        const uint32_t sb = wbase + (uint32_t)(c * 3 * RBLOCK);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                            for (int kk = 0; kk < CK / 16; ++kk) {
+                                const uint64_t ad = make_desc<CK>(sa + r * (SN_TILE_W * ROW_BYTES) + kk * 32);
+                                const uint64_t bd = make_desc<CK>(sb + r * RBLOCK + kk * 32);
+                                umma_bf16(d, ad, bd, idesc, (c | r | kk) != 0);
+                            }
+                        }
+                        umma_commit(empty_bar + st);
+                    }
+                    umma_commit(acc_full + buf);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue warps: TMEM lane quarter q = warp % 4 = image row q of the band; columns [c0, c0 + CW) --------
+        const int q = warp & 3, g = (warp - 2) >> 2;
+        const int c0 = g * CW;
+        const size_t plane = (size_t)a.H * a.W;
+        const int src2 = (lane + 30) & 31, src1 = (lane + 31) & 31;
+        const float m2 = lane < 2 ? 0.f : 1.f, m1 = lane < 1 ? 0.f : 1.f;     // lanes whose neighbours are in the previous tile
+        const bool w_full = a.W == a.tiles_x * SN_TILE_W;     // the band's last pixel is lane 31 of the last tile
+        // carries of this warp: rows 0 / 1 = Y_0 of lanes 30 / 31, row 2 = Y_1 (+ bias) of lane 31, row 3 = zeros
+        float* carry = s_carry + (size_t)(warp - 2) * 4 * CW;
+        const float4* cr0 = reinterpret_cast<const float4*>(carry + (lane == 0 ? 0 : CW));       // lane 0: rows 0 + 2; lane 1: rows 1 + 3
+        const float4* cr1 = reinterpret_cast<const float4*>(carry + (lane == 0 ? 2 * CW : 3 * CW));
+        if (lane < CW) carry[3 * CW + lane] = 0.f;
+        const float4* bias4 = reinterpret_cast<const float4*>(s_bias + c0);
+        // the epilogue variant is fixed for the launch: one flag instead of a chain of parameter loads and branches per tile
+        const bool plain = !a.out_nchw_f32 && a.out2 == nullptr && a.act_slope == 1.f && c0 + CW <= a.cout;
+        const bool stats = a.bn_sums != nullptr;
+        __syncwarp();
+
+        // one completed pixel per lane: activation, statistics, store
+        auto finish = [&](float (&o)[CW], float (&scratch)[CW], bool keep, int n_img, size_t px) {
+            if (!plain && a.act_slope != 1.f) {
+#pragma unroll
+                for (int i = 0; i < CW; ++i) o[i] = o[i] > 0.f ? o[i] : o[i] * a.act_slope;
+            }
+            if (stats) {
+                // BatchNorm statistics of the output (see conv_igemm_persistent_kernel), over the pixels COMPLETED here
+                const float kf = keep ? 1.f : 0.f;
+                const int col = c0 + ((lane >> 1) & 15);
+                const bool owner = (lane & 1) == 0;
+#pragma unroll
+                for (int i = 0; i < CW; ++i) scratch[i] = o[i] * kf;
+                const float cs = column_sums16(scratch, lane);
+                if (owner) s_stat[(q * 2 + 0) * NCO + col] += cs;
+#pragma unroll
+                for (int i = 0; i < CW; ++i) scratch[i] = o[i] * o[i] * kf;
+                const float cq = column_sums16(scratch, lane);
+                if (owner) s_stat[(q * 2 + 1) * NCO + col] += cq;
+            }
+            if (!keep) return;
+            if (plain) {
+                uint32_t pk[CW / 2];
+#pragma unroll
+                for (int i = 0; i < CW / 2; ++i) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + px * a.cout_stride + c0);
+#pragma unroll
+                for (int i = 0; i < CW / 8; ++i) o4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            } else if (a.out_nchw_f32) {
+                float* op = reinterpret_cast<float*>(a.out) + ((size_t)n_img * a.cout_real + c0) * plane + (px - (size_t)n_img * plane);
+                const int nlive = a.cout_real - c0;
+#pragma unroll
+                for (int i = 0; i < CW; ++i) { if (i >= nlive) break; *op = o[i]; op += plane; }
+            } else {
+                __nv_bfloat16* op;
+                if (a.out2 != nullptr) {
+                    const int rest = a.cpp - a.split;
+                    op = c0 < a.split ? reinterpret_cast<__nv_bfloat16*>(a.out) + px * (size_t)a.split + c0
+                                      : reinterpret_cast<__nv_bfloat16*>(a.out2) + px * (size_t)rest + (c0 - a.split);
+                } else {
+                    op = reinterpret_cast<__nv_bfloat16*>(a.out) + px * a.cout_stride + c0;
+                }
+                if (c0 + CW <= a.cout) {
+                    uint32_t pk[CW / 2];
+#pragma unroll
+                    for (int i = 0; i < CW / 2; ++i) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+                        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+                    for (int i = 0; i < CW / 8; ++i) o4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i)
+                        if (c0 + i < a.cout) op[i] = __float2bfloat16_rn(o[i]);
+                }
+            }
+        };
+
+        int tcount = 0;
+        for (int unit = blockIdx.x; unit < a.num_tiles; unit += gridDim.x) {
+            const int n_img = unit / a.tiles_y;
+            const int y = (unit - n_img * a.tiles_y) * SN_TILE_H + q;
+            const bool yvalid = y < a.H;
+            const size_t row_pix = ((size_t)n_img * a.H + y) * a.W;
+            for (int tx = 0; tx < a.tiles_x; ++tx, ++tcount) {
+                const int buf = tcount & 1;
+                const int x = tx * SN_TILE_W + lane - 1;       // the pixel this lane completes
+                mbar_wait_relaxed(acc_full + buf, (tcount >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float y0[CW], y1[CW], v[CW];
+                const uint32_t tb = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N3 + c0);
+                tmem_ld16_nowait(tb, y0); tmem_ld16_nowait(tb + NCO, y1); tmem_ld16_nowait(tb + 2 * NCO, v);
+                tmem_wait_ld(y0); tmem_ld_fence(y1); tmem_ld_fence(v);
+                // the accumulator is in registers: hand it back to the MMA issuer before the arithmetic
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + buf);
+#pragma unroll
+                for (int i = 0; i < CW / 4; ++i) {
+                    const float4 b = bias4[i];
+                    y1[4 * i] += b.x; y1[4 * i + 1] += b.y; y1[4 * i + 2] += b.z; y1[4 * i + 3] += b.w;
+                }
+#pragma unroll
+                for (int i = 0; i < CW; ++i) {
+                    const float a0 = __shfl_sync(0xffffffffu, y0[i], src2);
+                    const float a1 = __shfl_sync(0xffffffffu, y1[i], src1);
+                    v[i] = fmaf(a0, m2, fmaf(a1, m1, v[i]));
+                }
+                if (tx > 0 && lane < 2) {                      // the neighbours that sit in the previous tile
+#pragma unroll
+                    for (int i = 0; i < CW / 4; ++i) {
+                        const float4 c = cr0[i], d = cr1[i];
+                        v[4 * i] += c.x + d.x; v[4 * i + 1] += c.y + d.y; v[4 * i + 2] += c.z + d.z; v[4 * i + 3] += c.w + d.w;
+                    }
+                }
+                __syncwarp();
+                if (lane >= 30) {
+                    float4* w0 = reinterpret_cast<float4*>(carry + (lane - 30) * CW);
+#pragma unroll
+                    for (int i = 0; i < CW / 4; ++i) w0[i] = make_float4(y0[4 * i], y0[4 * i + 1], y0[4 * i + 2], y0[4 * i + 3]);
+                    if (lane == 31) {
+                        float4* w1 = reinterpret_cast<float4*>(carry + 2 * CW);
+#pragma unroll
+                        for (int i = 0; i < CW / 4; ++i) w1[i] = make_float4(y1[4 * i], y1[4 * i + 1], y1[4 * i + 2], y1[4 * i + 3]);
+                    }
+                }
+                __syncwarp();
+                const bool tail = w_full && tx == a.tiles_x - 1;                  // lane 31 also completes its own pixel
+                if (tail) {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) y1[i] += __shfl_sync(0xffffffffu, y0[i], src1);   // lane 31: Y_0[lane 30] + Y_1 + bias
+                }
+                finish(v, y0, yvalid && x >= 0 && x < a.W, n_img, row_pix + (size_t)x);
+                if (tail) finish(y1, y0, yvalid && lane == 31, n_img, row_pix + (size_t)x + 1);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+    if (a.bn_sums != nullptr && blockIdx.x < (unsigned)a.num_tiles) {
+        double* rep = a.bn_sums + (size_t)(blockIdx.x % a.bn_nrep) * 2 * a.bn_cstride;
+        for (int t = threadIdx.x; t < 2 * NCO; t += NTHREADS) {
+            const int which = t / NCO, c = t - which * NCO;
+            if (c < a.bn_cstride) {
+                const float tot = (s_stat[(0 + which) * NCO + c] + s_stat[(2 + which) * NCO + c]) +
+                                  (s_stat[(4 + which) * NCO + c] + s_stat[(6 + which) * NCO + c]);
+                atomicAdd(rep + (size_t)which * a.bn_cstride + c, (double)tot);
+            }
+        }
+    }
+}
+
 // ---- weight packing: torch [Cout][Cin][ks][ks] fp32 -> pre-swizzled bf16 stage images -----------------
 // dst block (nt, it = ((seg, chunk), s), r) is [n_tile][CK] bf16; 16-byte chunk j of row n is stored at
 // chunk (j ^ swz(n)) -- Swizzle<3|2|1,4,3> on the byte address, the pattern TMA / UMMA use.
@@ -525,6 +822,7 @@ struct PackArgs {
     int cout_mem;        // output channels per pixel in memory (pad16)
     int fold;            // F: the virtual conv works on [.., W/F, F*C] views
     int transpose;       // 1: logical W'[co][ci][r][s] = W[ci][co][ks-1-r][ks-1-s] (data-gradient conv)
+    int sn;              // 1: layout of conv_sn_kernel: block (chunk, r) = [3 * n_tile rows (s, co)][CK]
 };
 // logical (unfolded) weight of the convolution being packed
 __device__ __forceinline__ float logical_w(const PackArgs& p, int co, int ci, int r, int s) {
@@ -597,8 +895,16 @@ __device__ __forceinline__ void pack_weights_body(const PackArgs& p, long long f
                 v = logical_w(p, co, (seg == 0 ? 0 : p.seg_real[0]) + cl, r, s);
             vals[e] = __float2bfloat16_rn(v);
         }
-        const size_t block = (((size_t)nt * iters + it) * p.ks + r) * p.n_tile * (p.ck * 2);
-        const size_t off = block + (size_t)n * (p.ck * 2) + (size_t)((j ^ swz) * 16);
+        size_t off;
+        if (p.sn) {                                                     // (n_tiles = 1, F = 1, ks = 3)
+            const int np = dj * p.n_tile + n;                           // row (s, co) of the block of (chunk, r)
+            const int swz_sn = (np / span_rows) % chunks_per_row;
+            off = ((size_t)(it / p.ks) * p.ks + r) * (size_t)(p.ks * p.n_tile) * (p.ck * 2) + (size_t)np * (p.ck * 2) +
+                  (size_t)((j ^ swz_sn) * 16);
+        } else {
+            const size_t block = (((size_t)nt * iters + it) * p.ks + r) * p.n_tile * (p.ck * 2);
+            off = block + (size_t)n * (p.ck * 2) + (size_t)((j ^ swz) * 16);
+        }
         *reinterpret_cast<uint4*>(p.dst + off) = *reinterpret_cast<const uint4*>(vals);
     }
 }
@@ -618,8 +924,20 @@ using namespace uaps::conv;
 namespace {
 struct Plan {
     int ck, n_tile, n_tiles, seg_pad[2], chunks[2], nseg, iters;
+    int sn;              // 1: conv_sn_kernel (horizontal taps in N) and its weight layout
     size_t packed_bytes;
 };
+// conv_sn_kernel takes 3x3 layers with <= 64 (padded) output channels whose packed weights stay resident next to two
+// activation stages: every 16- / 32- / 64-channel layer of UNet_UAPS and the data gradients that produce them.
+// UAPS_CONV_SN=0 keeps those layers on conv_igemm_persistent_kernel (A/B profiling).
+constexpr size_t SN_W_MAX = 150 * 1024;
+inline bool sn_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("UAPS_CONV_SN");
+        return (e == nullptr || atoi(e) != 0) && getenv("UAPS_CONV_V1") == nullptr;
+    }();
+    return on;
+}
 // cin2 == 0: single segment.  Channels are zero-padded up to a multiple of 16 inside a segment; with pixel folding
 // (fold = F > 1) the plan is made for the virtual conv on the [.., W/F, F*C] views.
 int make_plan(int cout, int cin1, int cin2, int ks, int fold, Plan* pl) {
@@ -637,6 +955,13 @@ int make_plan(int cout, int cin1, int cin2, int ks, int fold, Plan* pl) {
     pl->n_tiles = (cout_v + pl->n_tile - 1) / pl->n_tile;
     pl->iters = (pl->chunks[0] + pl->chunks[1]) * ks;
     pl->packed_bytes = (size_t)pl->n_tiles * pl->iters * ks * pl->n_tile * ck * 2;
+    // ... and only where it wins (measured per layer, B = 64, profiles/r02_conv_sn_layers.txt): its epilogue reads three
+    // accumulator columns per output and is bound by issue slots at ~170 instructions per 32 x 16 fragment, so it pays when
+    // there is enough K behind every output column: input channels >= 2 x output channels, or >= 64.
+    const int cin_pad = pl->seg_pad[0] + (pl->nseg > 1 ? pl->seg_pad[1] : 0);
+    static const bool sn_all = [] { const char* e = getenv("UAPS_CONV_SN"); return e != nullptr && atoi(e) == 2; }();   // 2: every eligible layer
+    pl->sn = (sn_enabled() && ks == 3 && fold == 1 && pl->n_tiles == 1 && pl->n_tile <= 64 && pl->packed_bytes <= SN_W_MAX &&
+              (sn_all || cin_pad >= 2 * pl->n_tile || cin_pad >= 64)) ? 1 : 0;
     return UAPS_OK;
 }
 
@@ -693,7 +1018,7 @@ int make_pack_args(const float* w, void* w_packed, int cout, int cin1, int cin2,
     p.seg_mem[0] = (cin1 + 15) / 16 * 16; p.seg_mem[1] = (cin2 + 15) / 16 * 16;
     // unfolded outputs are addressed by real channel (stores beyond cout are masked); folded ones per padded pixel
     p.cout_mem = fold > 1 ? (cout + 15) / 16 * 16 : pl.n_tiles * pl.n_tile;
-    p.fold = fold; p.transpose = transpose;
+    p.fold = fold; p.transpose = transpose; p.sn = pl.sn;
     const long long total = (long long)pl.packed_bytes / 16;
     *grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     *out = p;
@@ -838,6 +1163,72 @@ int conv_fprop_impl(const void* x1, int c1_stride, const void* x2, int c2_stride
     const int a_bytes = (TILE_H + ks - 1) * TILE_W * row_bytes, b_bytes = ks * pl.n_tile * row_bytes;
     a.n_tiles = pl.n_tiles;
     a.num_tiles = a.tiles_x * a.tiles_y * B * pl.n_tiles;
+
+    if (pl.sn) {
+        // conv_sn_kernel: work unit = (image, band of 4 rows); resident weights; as many activation stages as fit the CTA's
+        // share of shared memory (the number of co-resident CTAs is set by their TMEM columns, at most 4)
+        a.tiles_x = (W + SN_TILE_W - 1) / SN_TILE_W; a.tiles_y = (H + SN_TILE_H - 1) / SN_TILE_H;
+        a.num_tiles = a.tiles_y * B; a.n_tiles = 1; a.resident = 1; a.xhalo = 0;
+        CUtensorMap m0, m1;
+        rc = encode_map(&m0, x1, B, H, W, c1_stride, pl.ck, SN_TILE_H + 2, SN_TILE_W);
+        if (rc != UAPS_OK) return rc;
+        rc = encode_map(&m1, cin2 > 0 ? x2 : x1, B, H, W, cin2 > 0 ? c2_stride : c1_stride, pl.ck, SN_TILE_H + 2, SN_TILE_W);
+        if (rc != UAPS_OK) return rc;
+        const int ng = pl.n_tile / 16;                      // epilogue warp groups (16 output channels each)
+        const int n3 = 3 * pl.n_tile;
+        int tmem_cols = 32;
+        while (tmem_cols < 2 * n3) tmem_cols <<= 1;
+        static const int cap_sn = [] { const char* e = getenv("UAPS_CONV_SN_CTAS_PER_SM"); return e ? atoi(e) : 4; }();
+        int per_sm = 512 / tmem_cols;
+        if (per_sm > cap_sn) per_sm = cap_sn;
+        if (per_sm < 1) per_sm = 1;
+        const size_t w_region = (pl.packed_bytes + 1023) & ~(size_t)1023;
+        const size_t stage_bytes = (size_t)(SN_TILE_H + 2) * SN_TILE_W * row_bytes;
+        // carries [epilogue warp][4][16] + bias [n_co] + statistics [4][2][n_co] floats
+        const size_t extra = (size_t)(4 * pl.n_tile * 4 + pl.n_tile + (bn_sums != nullptr ? 4 * 2 * pl.n_tile : 0)) * sizeof(float) + 1024;
+        static const int stages_sn = [] { const char* e = getenv("UAPS_CONV_SN_STAGES"); return e ? atoi(e) : 6; }();
+        int stages = stages_sn >= 2 && stages_sn <= MAX_STAGES ? stages_sn : 6;
+        for (;;) {
+            while (stages > 2 && w_region + stages * stage_bytes + extra + 2048 > (size_t)(227 * 1024) / per_sm) --stages;
+            if (w_region + stages * stage_bytes + extra + 2048 <= (size_t)(227 * 1024) / per_sm || per_sm == 1) break;
+            --per_sm;                                      // two stages do not fit this many CTAs: fewer CTAs, more stages
+            stages = stages_sn >= 2 && stages_sn <= MAX_STAGES ? stages_sn : 6;
+        }
+        a.stages = stages;
+        const size_t smem = w_region + stages * stage_bytes + extra;
+        if (smem > 227 * 1024) return UAPS_ERANGE;
+        cudaError_t e;
+        int occ = 0;
+        // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 for these kernels on B200 where 3 CTAs run: the CTAs per SM
+        // are derived from the kernel's register count instead)
+#define UAPS_CONV_LAUNCH3(CKV, NGV)                                                                                          \
+        e = cudaFuncSetAttribute(conv_sn_kernel<CKV, NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+        if (e != cudaSuccess) return (int)e;                                                                                     \
+        {                                                                                                                        \
+            static const int regs = [] {                                                                                         \
+                cudaFuncAttributes fa{};                                                                                         \
+                return cudaFuncGetAttributes(&fa, conv_sn_kernel<CKV, NGV>) == cudaSuccess ? fa.numRegs : 255;                   \
+            }();                                                                                                                 \
+            occ = 65536 / (((regs + 7) / 8 * 8) * SnCfg<NGV>::THREADS);                                                          \
+        }                                                                                                                        \
+        if (occ < 1) return UAPS_ERANGE;                                                                                         \
+        if (per_sm > occ) per_sm = occ;                    /* registers: the TMEM columns of more CTAs would never be freed */   \
+        if (getenv("UAPS_CONV_DEBUG") != nullptr)                                                                                \
+            fprintf(stderr, "conv_sn<%d,%d>: per_sm %d (regs allow %d) stages %d smem %zu units %d\n", CKV, NGV, per_sm, occ,     \
+                    stages, smem, a.num_tiles);                                                                                  \
+        gridx = (long long)device_info().sm_count * per_sm;                                                                      \
+        if (gridx > a.num_tiles) gridx = a.num_tiles;                                                                            \
+        UAPS_LAUNCH((conv_sn_kernel<CKV, NGV>), dim3((unsigned)gridx), dim3(SnCfg<NGV>::THREADS), smem, stream, m0, m1, a);
+#define UAPS_CONV_LAUNCH3_NG(CKV)                                                                       \
+        if (ng == 1) { UAPS_CONV_LAUNCH3(CKV, 1) } else if (ng == 2) { UAPS_CONV_LAUNCH3(CKV, 2) }         \
+        else if (ng == 3) { UAPS_CONV_LAUNCH3(CKV, 3) } else { UAPS_CONV_LAUNCH3(CKV, 4) }
+        long long gridx = 0;
+        if (pl.ck == 64) { UAPS_CONV_LAUNCH3_NG(64) } else if (pl.ck == 32) { UAPS_CONV_LAUNCH3_NG(32) } else { UAPS_CONV_LAUNCH3_NG(16) }
+#undef UAPS_CONV_LAUNCH3_NG
+#undef UAPS_CONV_LAUNCH3
+        UAPS_LAUNCH_CHECK();
+        return UAPS_OK;
+    }
 
     static const bool use_v1 = getenv("UAPS_CONV_V1") != nullptr;       // A/B knobs for profiling, not part of the ABI
     static const bool no_xhalo = getenv("UAPS_CONV_NO_XHALO") != nullptr;
