@@ -28,6 +28,8 @@
 // ring, warp 1 lane 0 = MMA issuer alternating between two TMEM accumulators, warps 2-5 = epilogue (tcgen05.ld -> + bias
 // [-> LeakyReLU] -> bf16 NHWC / fp32 NCHW), so tile i's epilogue overlaps tile i+1's MMAs.  Layers whose packed weights fit
 // 80 KB keep them resident in shared memory and load ONE x-halo activation box per channel chunk for all nine taps.
+// conv_sn_kernel (3x3 layers with <= 64 output channels and input channels >= 2x output channels or >= 64): the horizontal taps
+// in the MMA's N dimension -- every A tile is fetched 3 times instead of 9 -- and the pixel shift in the epilogue; see its header.
 // conv_igemm_kernel (UAPS_CONV_V1=1): the first, one-tile-per-CTA version, kept for A/B profiling.
 #include <cstdio>
 #include <cstdlib>
