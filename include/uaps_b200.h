@@ -265,6 +265,12 @@ int uaps_maxpool2_nhwc(const void* x, const void* gy, void* out, int B, int H, i
  * entry into the bf16 path for the network input (UAPS_train.py:177,185 feed NCHW fp32 batches) and for the
  * fp32 logits gradient coming back from the fused loss. */
 int uaps_nchw_f32_to_nhwc_bf16(const float* x, void* out, int B, int C, int H, int W, int Cp, cudaStream_t stream);
+/* The same for C <= 8 (the logits gradient), also accumulating the per-channel sums over all pixels of the bf16 values it
+ * writes -- the bias gradient of out_conv (utilities/UAPS_unet.py:138-139, through loss.backward() at UAPS_train.py:287):
+ * sums = uaps_nchw_f32_to_nhwc_bf16_sums_nrep() replicas of [Cp] doubles, zeroed by the caller; the total is their sum. */
+int uaps_nchw_f32_to_nhwc_bf16_sums_nrep(void);
+int uaps_nchw_f32_to_nhwc_bf16_sums(const float* x, void* out, int B, int C, int H, int W, int Cp, double* sums,
+                                    cudaStream_t stream);
 
 /* Fused train-mode BatchNorm2d + LeakyReLU(slope) + Dropout(p) on channels-last bf16 activations
  * (utilities/UAPS_unet.py:37-43: nn.BatchNorm2d -> nn.LeakyReLU() -> nn.Dropout(p)).  y: [npix, C] bf16,

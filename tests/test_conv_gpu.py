@@ -313,3 +313,39 @@ def test_sn_kernel_concat_and_split_over_several_tiles():
         a, b2 = conv(to_nhwc_bf16(dy), split=c)
         assert torch.equal(a, whole[..., :c]) and torch.equal(b2, whole[..., c:])
         assert (from_nhwc(whole, 2 * c) - x.grad).abs().max().item() <= 1e-2 * x.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 4, 40, 56), (2, 2, 64, 64), (1, 7, 17, 33), (2, 8, 16, 16)])
+def test_entry_conversion_with_bias_gradient_sums(B, C, H, W):
+    """uaps_nchw_f32_to_nhwc_bf16_sums: the same tensor as the plain conversion, and the per-channel sums of exactly the
+    bf16 values it holds (out_conv's bias gradient without a separate reduction pass)."""
+    from uaps_b200.conv import to_nhwc_bf16, to_nhwc_bf16_with_sums
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(B * 100 + C)
+    x = torch.randn(B, C, H, W, generator=g, device=dev) * 3.0
+    ref = to_nhwc_bf16(x)
+    out, sums = to_nhwc_bf16_with_sums(x)
+    assert torch.equal(out, ref)
+    want = ref[..., :C].double().sum((0, 1, 2))
+    assert sums.shape == (C,) and sums.dtype == torch.float32
+    torch.testing.assert_close(sums.double(), want, rtol=1e-5, atol=1e-4)
+
+
+def test_logits_conv_bias_gradient():
+    """out_conv through autograd: weight, bias and input gradients against fp32 torch on the bf16-rounded operands."""
+    from uaps_b200.conv import conv_bf16, to_nhwc_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 16, 48, 40, generator=g).to(dev)
+    w = (torch.randn(4, 16, 3, 3, generator=g) * 0.1).to(dev).requires_grad_(True)
+    b = torch.randn(4, generator=g).to(dev).requires_grad_(True)
+    gy = torch.randn(2, 4, 48, 40, generator=g).to(dev)
+    xc = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = conv_bf16(xc, w, b, nchw_f32_out=True)
+    y.backward(gy)
+    xr = x.bfloat16().float().requires_grad_(True)
+    wr, br = w.detach().bfloat16().float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    F.conv2d(xr, wr, br, padding=1).backward(gy)
+    assert (b.grad - br.grad).abs().max().item() <= 2e-2 * br.grad.abs().max().item()
+    assert (w.grad - wr.grad).abs().max().item() <= 1e-2 * wr.grad.abs().max().item()
+    assert (xc.grad.float() - xr.grad).abs().max().item() <= 1e-2 * xr.grad.abs().max().item()

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "uaps_upsample2x_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "uaps_maxpool2_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "uaps_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "uaps_nchw_f32_to_nhwc_bf16_sums_nrep": (_i, []),
+    "uaps_nchw_f32_to_nhwc_bf16_sums": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "uaps_bn_stats_nhwc": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "uaps_bn_act_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _d, _u64, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
     "uaps_conv_fprop_bn": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),

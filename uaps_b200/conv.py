@@ -31,6 +31,23 @@ def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def to_nhwc_bf16_with_sums(x: torch.Tensor):
+    """to_nhwc_bf16 of a tensor with <= 8 channels (the logits gradient) plus the per-channel sums over all pixels of the
+    bf16 values written (fp32 [C]) -- out_conv's bias gradient -- from the same kernel."""
+    L.require_cuda(x)
+    B, C, H, W = x.shape
+    x = x.float().contiguous()
+    cp = pad16(C)
+    out = torch.empty((B, H, W, cp), dtype=torch.bfloat16, device=x.device)
+    nrep = L.lib().uaps_nchw_f32_to_nhwc_bf16_sums_nrep()
+    sc = stepctx.current()
+    sums = sc.take(nrep * cp) if sc is not None else torch.zeros(nrep * cp, dtype=torch.float64, device=x.device)
+    with L.on_device(x.device):
+        L.check(L.lib().uaps_nchw_f32_to_nhwc_bf16_sums(x.data_ptr(), out.data_ptr(), B, C, H, W, cp, sums.data_ptr(),
+                                                        L.stream_ptr()), "uaps_nchw_f32_to_nhwc_bf16_sums")
+    return out, sums.view(nrep, cp)[:, :C].sum(0).float()
+
+
 def channel_sums(x_nhwc: torch.Tensor, c: int) -> torch.Tensor:
     """Per-channel sum over all pixels of a channels-last bf16 tensor (fp32 [c]): the bias gradient of a conv,
     by the BatchNorm statistics kernel (fp64 accumulation)."""
@@ -308,8 +325,12 @@ class _ConvFn(torch.autograd.Function):
     def backward(ctx, gy):
         x1, x2, weight = ctx.saved_tensors
         co, ci, ks, _ = weight.shape
+        gb_fused = None
         if ctx.nchw:                                         # fp32 NCHW logits gradient -> bf16 channels-last, 16-padded
-            gy_nhwc = to_nhwc_bf16(gy)
+            if ctx.has_bias and ctx.bias_grad and co <= 8:   # ... and out_conv's bias gradient from the same pass
+                gy_nhwc, gb_fused = to_nhwc_bf16_with_sums(gy)
+            else:
+                gy_nhwc = to_nhwc_bf16(gy)
         else:
             if not gy.is_contiguous(memory_format=torch.channels_last):
                 gy = gy.contiguous(memory_format=torch.channels_last)
@@ -348,7 +369,7 @@ class _ConvFn(torch.autograd.Function):
             # a bias in front of train-mode BatchNorm has an analytically zero gradient; only conv1x1 /
             # out_conv (bias_grad=True) need the reduction
             if ctx.bias_grad:
-                gb = channel_sums(gy_nhwc, co)
+                gb = gb_fused if gb_fused is not None else channel_sums(gy_nhwc, co)
             elif not direct:
                 gb = torch.zeros(co, dtype=torch.float32, device=gy.device)
         return g1, g2, gw, gb, None, None, None, None

@@ -187,6 +187,48 @@ __global__ void __launch_bounds__(RT) nchw_f32_to_nhwc_bf16_kernel(const float* 
     }
 }
 
+// The same conversion for the logits gradient, which also accumulates the per-channel sums of the (bf16-rounded) values it
+// writes -- the bias gradient of out_conv (UAPS_unet.py:138-139) -- so that the separate reduction pass over the padded
+// 16-channel tensor is not needed.  C <= 8; sums: NREP replicas of [Cp] doubles, zeroed by the caller (replica
+// blockIdx.x % NREP: same-address fp64 atomics serialise in L2).
+constexpr int ENTRY_NREP = 16;
+__global__ void __launch_bounds__(RT) nchw_f32_to_nhwc_bf16_sums_kernel(const float* __restrict__ x, uint4* __restrict__ out, int C,
+                                                                        int HW, int Gp, double* __restrict__ sums) {
+    __shared__ float s_part[RT / 32][8];
+    grid_dep_launch();
+    grid_dep_wait();
+    const int p = blockIdx.x * RT + threadIdx.x;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (p < HW) {
+        const float* xb = x + (size_t)blockIdx.y * C * HW + p;
+        uint4* ob = out + ((size_t)blockIdx.y * HW + p) * Gp;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < C) v[i] = __bfloat162float(__float2bfloat16_rn(__ldg(xb + (size_t)i * HW)));   // what the tensor will hold
+        ob[0] = pack8(v);
+        for (int g = 1; g < Gp; ++g) ob[g] = make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[warp][i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < RT / 32; ++w) t += s_part[w][threadIdx.x];
+        atomicAdd(sums + (size_t)(blockIdx.x % ENTRY_NREP) * (Gp * 8) + threadIdx.x, (double)t);
+    }
+}
+
 __global__ void __launch_bounds__(RT) maxpool2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int G) {
     grid_dep_launch();
     grid_dep_wait();
@@ -291,6 +333,20 @@ UAPS_API int uaps_nchw_f32_to_nhwc_bf16(const float* x, void* out, int B, int C,
     if (!aligned_to(x, 4) || !aligned_to(out, 16)) return UAPS_EALIGN;
     const int HW = H * W;
     UAPS_LAUNCH(nchw_f32_to_nhwc_bf16_kernel, dim3(ceil_div(HW, RT), B), dim3(RT), 0, stream, x, reinterpret_cast<uint4*>(out), C, HW, Cp / 8);
+    UAPS_LAUNCH_CHECK();
+    return UAPS_OK;
+}
+
+UAPS_API int uaps_nchw_f32_to_nhwc_bf16_sums_nrep(void) { return ENTRY_NREP; }
+
+UAPS_API int uaps_nchw_f32_to_nhwc_bf16_sums(const float* x, void* out, int B, int C, int H, int W, int Cp, double* sums,
+                                             cudaStream_t stream) {
+    if (x == nullptr || out == nullptr || sums == nullptr || B <= 0 || C <= 0 || H <= 0 || W <= 0) return UAPS_EINVAL;
+    if (C > 8 || Cp % 8 != 0 || Cp < C || B > 65535 || (long long)H * W >= 2147483647LL) return UAPS_ERANGE;
+    if (!aligned_to(x, 4) || !aligned_to(out, 16) || !aligned_to(sums, 8)) return UAPS_EALIGN;
+    const int HW = H * W;
+    UAPS_LAUNCH(nchw_f32_to_nhwc_bf16_sums_kernel, dim3(ceil_div(HW, RT), B), dim3(RT), 0, stream, x, reinterpret_cast<uint4*>(out), C,
+                HW, Cp / 8, sums);
     UAPS_LAUNCH_CHECK();
     return UAPS_OK;
 }
