@@ -11,6 +11,7 @@ namespace uaps {
 namespace {
 
 constexpr int PT = 256;
+constexpr int BG = 8;                       // batch samples per work item of perturb3_nhwc_kernel
 constexpr uint32_t kStreamNoise = 11, kStreamDrop = 12;
 
 struct Bf8 { uint4 raw; };
@@ -97,13 +98,25 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
     if (seed_dev != nullptr) seed += *seed_dev;       // device-resident step state (uaps_step_begin)
     if (u_dev != nullptr) u = *u_dev;
     const long long chunks_per_sample = HW * G;
-    const long long total = chunks_per_sample * B;
-    for (long long t = (long long)blockIdx.x * PT + threadIdx.x; t < total; t += (long long)gridDim.x * PT) {
-        const int b = (int)(t / chunks_per_sample);
-        const long long in_sample = t - (long long)b * chunks_per_sample;
+    // A work item = one in-sample position x a group of BG batch samples: the FeatureNoise draw is keyed by the in-sample
+    // index (UAPS_unet.py:178-179 samples ONE noise tensor of shape x.shape[1:] for the whole batch), so it is drawn once per
+    // item instead of once per sample -- the kernel is bound by the Philox arithmetic (ncu: 63 % issue-active at 56 % of the
+    // HBM rate), and this removes 7/16 of it.  The BG loads of an item are independent.
+    const int n_groups = (B + BG - 1) / BG;
+    const long long total = chunks_per_sample * n_groups;
+    for (long long w = (long long)blockIdx.x * PT + threadIdx.x; w < total; w += (long long)gridDim.x * PT) {
+        const int bg = (int)(w / chunks_per_sample);
+        const long long in_sample = w - (long long)bg * chunks_per_sample;
         const long long pix = in_sample / G;
-        float nz[8], kp[8];
+        float nz[8];
         uniform8(seed, (uint64_t)in_sample, kStreamNoise, nz);          // shared by the batch: keyed by the in-sample index
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nz[i] = (nz[i] * 2.f - 1.f) * range;
+        const int b_end = min(B, (bg + 1) * BG);
+#pragma unroll 2
+        for (int b = bg * BG; b < b_end; ++b) {
+        const long long t = (long long)b * chunks_per_sample + in_sample;
+        float kp[8];
         uniform8(seed, (uint64_t)t, kStreamDrop, kp);
         float m = 0.f;                                                   // FeatureDropout mask; its inputs exist only when that branch is live
         if ((BWD ? (const void*)g_fdrop : (const void*)y_fdrop) != nullptr) {
@@ -116,7 +129,7 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
             unpack8(__ldg(x + t), v);
             if (y_noise != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = fmaf(v[i], (nz[i] * 2.f - 1.f) * range, v[i]);
+                for (int i = 0; i < 8; ++i) o[i] = fmaf(v[i], nz[i], v[i]);
                 y_noise[t] = pack8(o);
             }
             if (y_drop != nullptr) {
@@ -136,7 +149,7 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
             if (g_noise != nullptr) {
                 unpack8(__ldg(g_noise + t), g);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = fmaf(g[i], (nz[i] * 2.f - 1.f) * range, g[i]);
+                for (int i = 0; i < 8; ++i) o[i] = fmaf(g[i], nz[i], g[i]);
             }
             if (g_drop != nullptr) {
                 unpack8(__ldg(g_drop + t), g);
@@ -161,6 +174,7 @@ __global__ void __launch_bounds__(PT) perturb3_nhwc_kernel(const uint4* __restri
                 for (int i = 0; i < 8; ++i) o[i] += g[i];
             }
             dx[t] = pack8(o);
+        }
         }
     }
 }
@@ -200,7 +214,7 @@ UAPS_API int uaps_perturb3_nhwc(const void* x, uint64_t seed, float noise_range,
     if (!valid_g(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
     if (!aligned_to(x, 16) || !aligned_to(y_noise, 16) || !aligned_to(y_drop, 16) || !aligned_to(y_fdrop, 16)) return UAPS_EALIGN;
     const float pk = (float)(1.0 - p_drop);
-    UAPS_LAUNCH(perturb3_nhwc_kernel<false>, dim3(grid1d(HW * (C / 8) * B)), dim3(PT), 0, stream,
+    UAPS_LAUNCH(perturb3_nhwc_kernel<false>, dim3(grid1d(HW * (C / 8) * ((B + BG - 1) / BG))), dim3(PT), 0, stream,
         reinterpret_cast<const uint4*>(x), (const uint4*)nullptr, (const uint4*)nullptr, (const uint4*)nullptr, seed, noise_range,
         (float)p_drop, (float)(1.0 / (double)pk), attention, smax_enc, u, reinterpret_cast<uint4*>(y_noise),
         reinterpret_cast<uint4*>(y_drop), reinterpret_cast<uint4*>(y_fdrop), (uint4*)nullptr, C / 8, (long long)HW, B, seed_dev, u_dev,
@@ -220,7 +234,7 @@ UAPS_API int uaps_perturb3_nhwc_bwd(const void* g_noise, const void* g_drop, con
     if (!valid_g(C) || !(p_drop >= 0.0 && p_drop < 1.0)) return UAPS_ERANGE;
     if (!aligned_to(dx, 16) || !aligned_to(g_noise, 16) || !aligned_to(g_drop, 16) || !aligned_to(g_fdrop, 16)) return UAPS_EALIGN;
     const float pk = (float)(1.0 - p_drop);
-    UAPS_LAUNCH(perturb3_nhwc_kernel<true>, dim3(grid1d(HW * (C / 8) * B)), dim3(PT), 0, stream,
+    UAPS_LAUNCH(perturb3_nhwc_kernel<true>, dim3(grid1d(HW * (C / 8) * ((B + BG - 1) / BG))), dim3(PT), 0, stream,
         (const uint4*)nullptr, reinterpret_cast<const uint4*>(g_noise), reinterpret_cast<const uint4*>(g_drop),
         reinterpret_cast<const uint4*>(g_fdrop), seed, noise_range, (float)p_drop, (float)(1.0 / (double)pk), attention, smax_enc, u,
         (uint4*)nullptr, (uint4*)nullptr, (uint4*)nullptr, reinterpret_cast<uint4*>(dx), C / 8, (long long)HW, B, seed_dev, u_dev,
