@@ -299,7 +299,6 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap map0, const __g
     const uint32_t tmem_d = tmem_base_smem;
     // everything above (barrier init, TMEM allocation) touched no global memory: it overlapped the predecessor's tail
     grid_dep_wait();
-    const int spatial = a.tiles_x * a.tiles_y;
 
     if (warp == 0) {
         if (lane == 0) {

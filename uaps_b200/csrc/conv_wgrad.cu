@@ -84,7 +84,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     const int b_bytes = (TILE_H + (a.fused_r ? 0 : halo)) * box_w * row_b;
     const int n_issuers = a.fused_r ? 1 : a.ks;
     const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
-    const int ntaps = a.ks * a.ks;
     // stride between the 128 / a_ch M groups: the second real box, or (fewer channels than M) one atom of the
     // same tile -- in bounds, finite, and its accumulator lanes are ignored
     const uint32_t lbo_dy = a.two_boxes ? (uint32_t)a_box : (uint32_t)(8 * row_a);   // N groups of dY (unused when one group)
