@@ -257,6 +257,12 @@ SN_SHAPES = [
     (2, 8, 64, 48, 16),        # three chunks of 16
     (1, 6, 40, 64, 4),         # 4 real output channels in a 16-column group
     (1, 4, 31, 80, 48),        # five chunks of 16; a single ragged tile
+    # conv_sn_small_kernel (<= 5 output channels: the logits layer; all taps of all classes in one 16-column group)
+    (2, 9, 100, 16, 2),
+    (1, 7, 96, 32, 3),
+    (2, 5, 33, 16, 5),
+    (1, 8, 64, 16, 1),
+    (2, 6, 72, 16, 4),
 ]
 
 

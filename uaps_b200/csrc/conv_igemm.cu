@@ -30,6 +30,8 @@
 // 80 KB keep them resident in shared memory and load ONE x-halo activation box per channel chunk for all nine taps.
 // conv_sn_kernel (3x3 layers with <= 64 output channels and input channels >= 2x output channels or >= 64): the horizontal taps
 // in the MMA's N dimension -- every A tile is fetched 3 times instead of 9 -- and the pixel shift in the epilogue; see its header.
+// conv_sn_small_kernel (3x3 layers with <= 5 output channels: the logits layer): the same with all taps of all classes in one
+// 16-column accumulator group.
 // conv_igemm_kernel (UAPS_CONV_V1=1): the first, one-tile-per-CTA version, kept for A/B profiling.
 #include <cstdio>
 #include <cstdlib>
@@ -812,6 +814,209 @@ conv_sn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__
     }
 }
 
+// ---- v3 for the logits layer: C <= 5 output channels -------------------------------------------------------------
+// out_conv (UAPS_unet.py:138-139) has 16 input and 2..4 output channels: with the horizontal taps in N all three taps of all
+// classes fit ONE 16-column accumulator group (column s * C + c), so a tile is 3 MMAs of N = 16 and the epilogue reads 16
+// TMEM columns and does 2 C shuffles per pixel instead of 48 / 32.  Same tiles, carries and roles as conv_sn_kernel.
+// Rows 3 C .. 15 of the packed weight blocks are never written (their accumulator columns are never read).
+template <int CK, int C>
+__global__ void __launch_bounds__(192, 4)
+conv_sn_small_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                     const __grid_constant__ ConvArgs a) {
+    constexpr int ROW_BYTES = CK * 2;
+    constexpr int A_BYTES = (SN_TILE_H + 2) * SN_TILE_W * ROW_BYTES;
+    constexpr int N3 = 16, NTHREADS = 192, CP = 8;                             // CP: carry / bias / statistics row pitch (floats)
+    constexpr int RBLOCK = N3 * ROW_BYTES;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2], w_bar;
+    __shared__ uint32_t tmem_base_smem;
+    grid_dep_launch();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = a.chunks[0] + (a.nseg > 1 ? a.chunks[1] : 0);
+    const int w_total = chunks * 3 * RBLOCK;
+    const int w_region = (w_total + 1023) & ~1023;
+    unsigned char* stage0 = smem + w_region;
+    float* s_carry = reinterpret_cast<float*>(stage0 + (size_t)a.stages * A_BYTES);   // [epilogue warp][3][CP]
+    float* s_bias = s_carry + 4 * 3 * CP;                                              // [CP]
+    float* s_stat = s_bias + CP;                                                       // [lane quarter][sum | sumsq][CP]
+    if (threadIdx.x < CP) s_bias[threadIdx.x] = (a.bias != nullptr && (int)threadIdx.x < C) ? a.bias[threadIdx.x] : 0.f;
+    if (a.bn_sums != nullptr && threadIdx.x < 4 * 2 * CP) s_stat[threadIdx.x] = 0.f;
+    constexpr uint32_t tmem_cols = 32;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 4); }
+        mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+    grid_dep_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer (as conv_sn_kernel) ----------------------------------------------------
+            mbar_expect_tx(&w_bar, w_total);
+            for (int off = 0; off < w_total; off += 16384)
+                bulk_g2s(smem + off, a.w_packed + off, min(16384, w_total - off), &w_bar);
+            int itg = 0;
+            for (int unit = blockIdx.x; unit < a.num_tiles; unit += gridDim.x) {
+                const int n_img = unit / a.tiles_y, y0 = (unit - n_img * a.tiles_y) * SN_TILE_H;
+                for (int tx = 0; tx < a.tiles_x; ++tx) {
+                    for (int seg = 0; seg < a.nseg; ++seg) {
+                        const CUtensorMap* map = seg == 0 ? &map0 : &map1;
+                        for (int ch = 0; ch < a.chunks[seg]; ++ch, ++itg) {
+                            const int st = itg % a.stages;
+                            mbar_wait_relaxed(empty_bar + st, ((itg / a.stages) & 1) ^ 1);
+                            mbar_expect_tx(full_bar + st, A_BYTES);
+                            tma_load_4d(stage0 + (size_t)st * A_BYTES, map, ch * CK, tx * SN_TILE_W, y0 - 1, n_img, full_bar + st);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer (as conv_sn_kernel, N = 16) ------------------------------------------------
+            const uint32_t idesc = make_idesc(N3);
+            const uint32_t wbase = smem_u32(smem);
+            mbar_wait(&w_bar, 0);
+            int itg = 0, tcount = 0;
+            for (int unit = blockIdx.x; unit < a.num_tiles; unit += gridDim.x) {
+                for (int tx = 0; tx < a.tiles_x; ++tx, ++tcount) {
+                    const int buf = tcount & 1;
+                    mbar_wait(acc_empty + buf, ((tcount >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d = tmem_d + (uint32_t)(buf * N3);
+                    for (int c = 0; c < chunks; ++c, ++itg) {
+                        const int st = itg % a.stages;
+                        mbar_wait(full_bar + st, (itg / a.stages) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = smem_u32(stage0 + (size_t)st * A_BYTES);
+                        const uint32_t sb = wbase + (uint32_t)(c * 3 * RBLOCK);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                            for (int kk = 0; kk < CK / 16; ++kk) {
+                                const uint64_t ad = make_desc<CK>(sa + r * (SN_TILE_W * ROW_BYTES) + kk * 32);
+                                const uint64_t bd = make_desc<CK>(sb + r * RBLOCK + kk * 32);
+                                umma_bf16(d, ad, bd, idesc, (c | r | kk) != 0);
+                            }
+                        }
+                        umma_commit(empty_bar + st);
+                    }
+                    umma_commit(acc_full + buf);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue warps 2..5: image row q of the band, all C channels ------------------------------------------
+        const int q = warp & 3;
+        const size_t plane = (size_t)a.H * a.W;
+        const int src2 = (lane + 30) & 31, src1 = (lane + 31) & 31;
+        const float m2 = lane < 2 ? 0.f : 1.f, m1 = lane < 1 ? 0.f : 1.f;
+        const bool w_full = a.W == a.tiles_x * SN_TILE_W;
+        float* carry = s_carry + (size_t)(warp - 2) * 3 * CP;      // rows: Y_0 of lane 30, Y_0 of lane 31, Y_1 (+ bias) of lane 31
+        float bias[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) bias[c] = s_bias[c];
+        const bool stats = a.bn_sums != nullptr;
+        __syncwarp();
+
+        auto finish = [&](float (&o)[C], bool keep, int n_img, size_t px) {
+            if (a.act_slope != 1.f) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) o[c] = o[c] > 0.f ? o[c] : o[c] * a.act_slope;
+            }
+            if (stats) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float s1 = keep ? o[c] : 0.f, s2 = s1 * s1;
+#pragma unroll
+                    for (int sh = 16; sh > 0; sh >>= 1) {
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
+                    }
+                    if (lane == 0) { s_stat[(q * 2 + 0) * CP + c] += s1; s_stat[(q * 2 + 1) * CP + c] += s2; }
+                }
+            }
+            if (!keep) return;
+            if (a.out_nchw_f32) {
+                float* op = reinterpret_cast<float*>(a.out) + (size_t)n_img * a.cout_real * plane + (px - (size_t)n_img * plane);
+#pragma unroll
+                for (int c = 0; c < C; ++c) { *op = o[c]; op += plane; }
+            } else {
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + px * a.cout_stride;
+#pragma unroll
+                for (int c = 0; c < C; ++c) op[c] = __float2bfloat16_rn(o[c]);
+            }
+        };
+
+        int tcount = 0;
+        for (int unit = blockIdx.x; unit < a.num_tiles; unit += gridDim.x) {
+            const int n_img = unit / a.tiles_y;
+            const int y = (unit - n_img * a.tiles_y) * SN_TILE_H + q;
+            const bool yvalid = y < a.H;
+            const size_t row_pix = ((size_t)n_img * a.H + y) * a.W;
+            for (int tx = 0; tx < a.tiles_x; ++tx, ++tcount) {
+                const int buf = tcount & 1;
+                const int x = tx * SN_TILE_W + lane - 1;       // the pixel this lane completes
+                mbar_wait_relaxed(acc_full + buf, (tcount >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N3), v);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + buf);
+                float o[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    v[C + c] += bias[c];
+                    const float a0 = __shfl_sync(0xffffffffu, v[c], src2);
+                    const float a1 = __shfl_sync(0xffffffffu, v[C + c], src1);
+                    o[c] = fmaf(a0, m2, fmaf(a1, m1, v[2 * C + c]));
+                }
+                if (tx > 0 && lane < 2) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) o[c] += lane == 0 ? carry[c] + carry[2 * CP + c] : carry[CP + c];
+                }
+                __syncwarp();
+                if (lane >= 30) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        carry[(lane - 30) * CP + c] = v[c];
+                        if (lane == 31) carry[2 * CP + c] = v[C + c];
+                    }
+                }
+                __syncwarp();
+                const bool tail = w_full && tx == a.tiles_x - 1;
+                finish(o, yvalid && x >= 0 && x < a.W, n_img, row_pix + (size_t)x);
+                if (tail) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) o[c] = __shfl_sync(0xffffffffu, v[c], src1) + v[C + c];
+                    finish(o, yvalid && lane == 31, n_img, row_pix + (size_t)x + 1);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, tmem_cols);
+    if (a.bn_sums != nullptr && blockIdx.x < (unsigned)a.num_tiles && threadIdx.x < 2 * C) {
+        const int which = threadIdx.x / C, c = threadIdx.x - which * C;
+        double* rep = a.bn_sums + (size_t)(blockIdx.x % a.bn_nrep) * 2 * a.bn_cstride;
+        const float tot = (s_stat[(0 + which) * CP + c] + s_stat[(2 + which) * CP + c]) +
+                          (s_stat[(4 + which) * CP + c] + s_stat[(6 + which) * CP + c]);
+        atomicAdd(rep + (size_t)which * a.bn_cstride + c, (double)tot);
+    }
+}
+
 // ---- weight packing: torch [Cout][Cin][ks][ks] fp32 -> pre-swizzled bf16 stage images -----------------
 // dst block (nt, it = ((seg, chunk), s), r) is [n_tile][CK] bf16; 16-byte chunk j of row n is stored at
 // chunk (j ^ swz(n)) -- Swizzle<3|2|1,4,3> on the byte address, the pattern TMA / UMMA use.
@@ -823,7 +1028,7 @@ struct PackArgs {
     int cout_mem;        // output channels per pixel in memory (pad16)
     int fold;            // F: the virtual conv works on [.., W/F, F*C] views
     int transpose;       // 1: logical W'[co][ci][r][s] = W[ci][co][ks-1-r][ks-1-s] (data-gradient conv)
-    int sn;              // 1: layout of conv_sn_kernel: block (chunk, r) = [3 * n_tile rows (s, co)][CK]
+    int sn;              // 1: layout of conv_sn_kernel: block (chunk, r) = [3 * n_tile rows (s, co)][CK]; 2: conv_sn_small_kernel
 };
 // logical (unfolded) weight of the convolution being packed
 __device__ __forceinline__ float logical_w(const PackArgs& p, int co, int ci, int r, int s) {
@@ -897,7 +1102,12 @@ __device__ __forceinline__ void pack_weights_body(const PackArgs& p, long long f
             vals[e] = __float2bfloat16_rn(v);
         }
         size_t off;
-        if (p.sn) {                                                     // (n_tiles = 1, F = 1, ks = 3)
+        if (p.sn == 2) {                                                // conv_sn_small_kernel: 16-row blocks, row s * C + co
+            if (n >= p.cout_real) continue;
+            const int np = dj * p.cout_real + n;
+            const int swz_sn = (np / span_rows) % chunks_per_row;
+            off = ((size_t)(it / p.ks) * p.ks + r) * (size_t)16 * (p.ck * 2) + (size_t)np * (p.ck * 2) + (size_t)((j ^ swz_sn) * 16);
+        } else if (p.sn) {                                              // (n_tiles = 1, F = 1, ks = 3)
             const int np = dj * p.n_tile + n;                           // row (s, co) of the block of (chunk, r)
             const int swz_sn = (np / span_rows) % chunks_per_row;
             off = ((size_t)(it / p.ks) * p.ks + r) * (size_t)(p.ks * p.n_tile) * (p.ck * 2) + (size_t)np * (p.ck * 2) +
@@ -925,7 +1135,7 @@ using namespace uaps::conv;
 namespace {
 struct Plan {
     int ck, n_tile, n_tiles, seg_pad[2], chunks[2], nseg, iters;
-    int sn;              // 1: conv_sn_kernel (horizontal taps in N) and its weight layout
+    int sn;              // 1: conv_sn_kernel (horizontal taps in N) and its weight layout; 2: conv_sn_small_kernel (cout <= 5)
     size_t packed_bytes;
 };
 // conv_sn_kernel takes 3x3 layers with <= 64 (padded) output channels whose packed weights stay resident next to two
@@ -963,6 +1173,7 @@ int make_plan(int cout, int cin1, int cin2, int ks, int fold, Plan* pl) {
     static const bool sn_all = [] { const char* e = getenv("UAPS_CONV_SN"); return e != nullptr && atoi(e) == 2; }();   // 2: every eligible layer
     pl->sn = (sn_enabled() && ks == 3 && fold == 1 && pl->n_tiles == 1 && pl->n_tile <= 64 && pl->packed_bytes <= SN_W_MAX &&
               (sn_all || cin_pad >= 2 * pl->n_tile || cin_pad >= 64)) ? 1 : 0;
+    if (sn_enabled() && ks == 3 && fold == 1 && cout <= 5 && pl->packed_bytes <= SN_W_MAX) pl->sn = 2;    // the logits layer
     return UAPS_OK;
 }
 
@@ -1175,6 +1386,38 @@ int conv_fprop_impl(const void* x1, int c1_stride, const void* x2, int c2_stride
         if (rc != UAPS_OK) return rc;
         rc = encode_map(&m1, cin2 > 0 ? x2 : x1, B, H, W, cin2 > 0 ? c2_stride : c1_stride, pl.ck, SN_TILE_H + 2, SN_TILE_W);
         if (rc != UAPS_OK) return rc;
+        if (pl.sn == 2) {
+            if (out2 != nullptr) return UAPS_EINVAL;                   // (a split output needs >= 32 channels)
+            const size_t w_region = ((size_t)(pl.chunks[0] + pl.chunks[1]) * 3 * 16 * row_bytes + 1023) & ~(size_t)1023;
+            const size_t stage_bytes = (size_t)(SN_TILE_H + 2) * SN_TILE_W * row_bytes;
+            const size_t extra = (size_t)(4 * 3 * 8 + 8 + 4 * 2 * 8) * sizeof(float) + 1024;
+            int per_sm = 4, stages = 6;
+            while (stages > 2 && w_region + stages * stage_bytes + extra + 2048 > (size_t)(227 * 1024) / per_sm) --stages;
+            while (per_sm > 1 && w_region + stages * stage_bytes + extra + 2048 > (size_t)(227 * 1024) / per_sm) --per_sm;
+            a.stages = stages;
+            const size_t smem = w_region + stages * stage_bytes + extra;
+            if (smem > 227 * 1024) return UAPS_ERANGE;
+            long long gridx = (long long)device_info().sm_count * per_sm;
+            if (gridx > a.num_tiles) gridx = a.num_tiles;
+            cudaError_t e;
+#define UAPS_CONV_LAUNCH4(CKV, CV)                                                                                          \
+            e = cudaFuncSetAttribute(conv_sn_small_kernel<CKV, CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+            if (e != cudaSuccess) return (int)e;                                                                            \
+            UAPS_LAUNCH((conv_sn_small_kernel<CKV, CV>), dim3((unsigned)gridx), dim3(192), smem, stream, m0, m1, a);
+#define UAPS_CONV_LAUNCH4_C(CKV)                                                                   \
+            switch (cout_real) {                                                                   \
+                case 1: { UAPS_CONV_LAUNCH4(CKV, 1) } break;                                       \
+                case 2: { UAPS_CONV_LAUNCH4(CKV, 2) } break;                                       \
+                case 3: { UAPS_CONV_LAUNCH4(CKV, 3) } break;                                       \
+                case 4: { UAPS_CONV_LAUNCH4(CKV, 4) } break;                                       \
+                default: { UAPS_CONV_LAUNCH4(CKV, 5) } break;                                      \
+            }
+            if (pl.ck == 64) { UAPS_CONV_LAUNCH4_C(64) } else if (pl.ck == 32) { UAPS_CONV_LAUNCH4_C(32) } else { UAPS_CONV_LAUNCH4_C(16) }
+#undef UAPS_CONV_LAUNCH4_C
+#undef UAPS_CONV_LAUNCH4
+            UAPS_LAUNCH_CHECK();
+            return UAPS_OK;
+        }
         const int ng = pl.n_tile / 16;                      // epilogue warp groups (16 output channels each)
         const int n3 = 3 * pl.n_tile;
         int tmem_cols = 32;
