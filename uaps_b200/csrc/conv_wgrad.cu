@@ -20,6 +20,7 @@
 //     the dY tile shifted by g rows (LBO = one box row): one MMA per 16-pixel k-step (N = 3 * Cout) instead of three.
 // The accumulators (ks x Cout fp32 columns) stay in TMEM across all pixel tiles of the CTA (split-K over CTAs), then are
 // added to dW with fp32 reductions.  The TMA -> MMA ring is 8 / 6 / 3 stages deep for 16 / 32 / wider channel chunks.
+#include <cstdio>
 #include <cstdlib>
 #include "tc_common.cuh"
 
@@ -368,7 +369,8 @@ int plan_wgrad(int B, int H, int W, int cout, int cin, int cin_total, int ci_off
     const int stage_sz = (a_bytes + b_bytes + 1023) & ~1023;
     // measured (B=64, tools/gpu_probe_layers.py): 3x3 16-channel layers 100 -> 86 us with 8 stages, 32-channel 62.5 -> 58.4 us
     // with 6; the 1x1 and >= 64-channel layers are best at 3 (deeper rings only cost them resident CTAs)
-    const int auto_stages = ks == 3 && stage_sz <= 12 * 1024 ? 8 : (ks == 3 && stage_sz <= 24 * 1024 ? 6 : 3);
+    // (>= 64 channels, 3x3: these run one CTA per SM whatever the ring depth -- 4 stages: 38.7 -> 36.4 us on 64 -> 64 @64x64)
+    const int auto_stages = ks == 3 && stage_sz <= 12 * 1024 ? 8 : (ks == 3 && stage_sz <= 24 * 1024 ? 6 : (ks == 3 ? 4 : 3));
     a.stages = stages_env >= 2 && stages_env <= MAX_STAGES ? stages_env : auto_stages;
     while (a.stages > 2 && (size_t)a.stages * stage_sz > 200 * 1024) --a.stages;
     pl->smem = (size_t)a.stages * stage_sz + 1024;
@@ -398,10 +400,11 @@ int plan_wgrad(int B, int H, int W, int cout, int cin, int cin_total, int ci_off
         const double t = waves * per_cta * tile_us + sp * red_per_split_us + (ws_mode ? 6.0 : 3.0);
         if (t < best_t) { best_t = t; best = sp; }
     }
-    // the largest single-wave split count is always a candidate in workspace mode (the geometric search may step over it)
-    if (ws_mode && slots / a.groups >= 1) {
+    // the largest single-wave split count is always a candidate (the geometric search may step over it: 121 -> 151 left
+    // 27 of 148 SMs idle on the 32-channel layers)
+    if (slots / a.groups >= 1) {
         const int sp = slots / a.groups < a.tiles_total ? slots / a.groups : a.tiles_total;
-        const double t = ((a.tiles_total + sp - 1) / sp) * tile_us + sp * red_per_split_us + 6.0;
+        const double t = ((a.tiles_total + sp - 1) / sp) * tile_us + sp * red_per_split_us + (ws_mode ? 6.0 : 3.0);
         if (t < best_t) { best_t = t; best = sp; }
     }
     a.tiles_per_cta = (a.tiles_total + best - 1) / best;
@@ -442,6 +445,7 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
         cudaError_t eo = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         if (eo == cudaSuccess) eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_wgrad_kernel, THREADS, pl.smem);
         if (eo != cudaSuccess || occ < 1) { (void)cudaGetLastError(); ws_mode = false; }
+        if (getenv("UAPS_CONV_DEBUG") != nullptr) fprintf(stderr, "wgrad occupancy API: %d CTAs/SM at %zu B smem\n", occ, pl.smem);
         rc = plan_wgrad(B, H, W, cout, cin, cin_total, ci_offset, ks, ws_mode, &pl, ws_mode ? occ : 0);
         if (rc != UAPS_OK) return rc;
     }
@@ -465,6 +469,9 @@ UAPS_API int uaps_conv_wgrad(const void* dy, int dy_c_stride, const void* x, int
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)pl.splits, (unsigned)pl.n_chunks, (unsigned)pl.m_tiles);
+    if (getenv("UAPS_CONV_DEBUG") != nullptr)
+        fprintf(stderr, "wgrad %dx%d cout %d cin %d ks %d: ws %d splits %d groups %d tiles/cta %d stages %d smem %zu m_rows %d fused_r %d\n",
+                H, W, cout, cin, ks, (int)ws_mode, pl.splits, a.groups, a.tiles_per_cta, a.stages, pl.smem, a.m_rows, a.fused_r);
     if (ws_mode) {
         // The grid barrier needs every CTA resident at once: it is launched as a COOPERATIVE kernel, which the driver
         // refuses (instead of deadlocking) when the grid cannot be co-resident.
